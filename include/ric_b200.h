@@ -1,0 +1,127 @@
+/* ric_b200.h -- C ABI of the B200-native RIC transform+quantisation front end.
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of rududu/RIC:
+ *   colour / level shift      src/ric/ric.cpp:76-112,143-148,227-246
+ *   CWavelet2D::Transform     src/lib/wavelet2d.cpp:926-958  (+Transform97/53 :407-492,:636-692)
+ *   CBandCodec::buildTree     src/lib/bandcodec.cpp:239-322  (encode quantiser, folded output)
+ *   CBand::TSUQ / TSUQi       src/lib/band.h:65-107
+ *   CWavelet2D::TransformI    src/lib/wavelet2d.cpp:960-992  (+Transform97I/53I :494-591,:694-764)
+ * The reference has no FFI layer: its boundary is the C++ class API (CWavelet2D/CBand).  The C++
+ * shim in include/rududu_b200/ re-creates those classes on top of the functions declared here;
+ * INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a negative RIC_E_* code (never throws).
+ * All kernels are hand-written sm_100a CUDA; there is NO CPU fallback: if no CUDA device is
+ * usable, ric_create fails with RIC_E_CUDA.
+ *
+ * Band ("canonical") order used everywhere: id = 3*lev + {0:D, 1:H, 2:V}, lev 0 = finest level,
+ * id = 3*nlev = the coarsest level's LL band.  A plane's bands live in one "arena": each band
+ * row-major with the reference's DimXAlign stride (band.cpp:57) at a 32-byte aligned offset --
+ * exactly the buffers the reference's entropy stage (CBandCodec::pred/tree) consumes.
+ * An image with C planes has C consecutive arenas, plane order = CImg channel order after the
+ * colour transform: 0 = Co, 1 = Cg, 2 = Y (ric.cpp:76-91), or the single gray plane.
+ */
+#ifndef RIC_B200_H
+#define RIC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIC_MAX_LEVELS 16
+#define RIC_MAX_BANDS (3 * RIC_MAX_LEVELS + 1)
+
+enum { RIC_CDF97 = 0, RIC_CDF53 = 1, RIC_HAAR = 2 }; /* enum trans, src/lib/utils.h:28 */
+
+enum {
+	RIC_OK = 0,
+	RIC_E_ARG = -1,      /* invalid argument / unsupported geometry */
+	RIC_E_CUDA = -2,     /* CUDA runtime error (ric_last_error() has the text) */
+	RIC_E_NOMEM = -3,
+	RIC_E_UNSUPPORTED = -4
+};
+
+typedef struct ric_ctx ric_ctx;
+
+typedef struct {
+	int dimx, dimy;   /* CBand::DimX, DimY       band.h:43-44 */
+	int stride;       /* CBand::DimXAlign        band.cpp:57 (samples) */
+	int is_int;       /* band_t sint             band.h:35 */
+	float weight;     /* CBand::Weight           wavelet2d.cpp:1009-1032 */
+	size_t offset;    /* byte offset inside one plane arena */
+} ric_band_info;
+
+typedef struct {
+	int width, height, channels;
+	int levels, level_chg, align, trans;
+	int nlev;          /* levels actually built (wavelet2d.cpp:76) */
+	int nbands;        /* 3*nlev + 1 */
+	int max_batch;
+	size_t arena_bytes;       /* one plane */
+	size_t image_arena_bytes; /* channels * arena_bytes */
+} ric_info;
+
+/* ---- context -------------------------------------------------------------------------------
+ * Replaces CWavelet2D::CWavelet2D / Init (wavelet2d.cpp:38-81), CBand::Init (band.cpp:51-65) and
+ * SetWeight (wavelet2d.cpp:1009-1032) for `channels` planes of up to `max_batch` images on CUDA
+ * device `device`.  trans selects the lifting (cdf97, cdf53; haar is RIC_E_UNSUPPORTED on GPU). */
+int ric_create(ric_ctx **out, int device, int width, int height, int channels, int levels,
+               int level_chg, int align, int trans, int max_batch);
+int ric_destroy(ric_ctx *ctx);
+int ric_get_info(const ric_ctx *ctx, ric_info *info);
+int ric_get_band(const ric_ctx *ctx, int band_id, ric_band_info *info);
+const char *ric_last_error(void);
+
+/* Quants(), ric.cpp:42-49, and the per-plane (Quant, lambda) pair ric derives from -q
+ * (ric.cpp:163-171): plane `plane` of `channels`. */
+int ric_quants(int idx);
+int ric_plane_quant(int q, int channels, int plane, int *Quant, int *lambda);
+
+/* ---- whole-stage entry points, HOST buffers (H2D + kernels + D2H inside) ---------------------
+ * ric_encode_u8: what CompressImage does between loading the image and the first entropy call:
+ *   colour/level shift + Transform + buildTree x3 + LL TSUQ for every plane of n images.
+ *   src: n planar u8 images (channels*height*width each, densely packed).
+ *   arenas: n * image_arena_bytes, filled with quantised bands ready for CBandCodec::pred/tree.
+ *   q: ric's -q value 0..31 (0 = lossless: only folding).  Quant/lambda as ric.cpp:163-171.
+ * ric_decode_u8: what DecompressImage does after the last DecodeBand: TSUQi + TransformI +
+ *   inverse colour + clip.  arenas hold signed quantised coefficients (DecodeBand output). */
+int ric_encode_u8(ric_ctx *ctx, const uint8_t *src, int n, int q, void *arenas);
+int ric_decode_u8(ric_ctx *ctx, const void *arenas, int n, int q, uint8_t *dst);
+
+/* ---- device-resident variants (no copies; asynchronous on `stream`, a cudaStream_t) ------------
+ * d_src pitch: bytes between rows (multiple of 8); planes are pitch*height apart, images
+ * channels*pitch*height apart.  d_arenas as above but in device memory.  d_dst likewise. */
+int ric_encode_u8_device(ric_ctx *ctx, const uint8_t *d_src, size_t pitch, int n, int q,
+                         void *d_arenas, void *stream);
+int ric_decode_u8_device(ric_ctx *ctx, const void *d_arenas, int n, int q, uint8_t *d_dst,
+                         size_t pitch, void *stream);
+/* number of kernel launches the last *_device call enqueued (for bench accounting) */
+int ric_last_launch_count(const ric_ctx *ctx);
+
+/* ---- plane-level entry points mirroring the reference class API (HOST buffers) -------------------
+ * One plane at a time on batch slot 0, like a CWavelet2D object:
+ * ric_transform:   CWavelet2D::Transform<short>(pImage, Stride, t)  wavelet2d.cpp:926.
+ *                  Unlike the reference the caller's plane is left untouched. arena receives the
+ *                  unquantised bands (may be NULL to keep them on the device only).
+ * ric_quant:       the quantiser half of CodeBand (wavelet2d.cpp:110-126): buildTree x3 + LL
+ *                  TSUQ(0.5) on the device-resident bands of the last ric_transform; result -> arena.
+ * ric_tsuq:        CWavelet2D::TSUQ(Quant, Thres)   wavelet2d.cpp:224-246; *count gets Count.
+ * ric_tsuqi:       CWavelet2D::TSUQi(Quant)          wavelet2d.cpp:248-268 on arena (in/out, host).
+ * ric_transform_inv: CWavelet2D::TransformI wavelet2d.cpp:960; takes the plane START (not the
+ *                  one-past-end pointer of the reference) and reads the bands from arena. */
+int ric_transform(ric_ctx *ctx, const int16_t *plane, int stride, void *arena);
+int ric_quant(ric_ctx *ctx, int Quant, int lambda, void *arena);
+int ric_tsuq(ric_ctx *ctx, int Quant, float thres, void *arena, unsigned *count);
+int ric_tsuqi(ric_ctx *ctx, int Quant, void *arena);
+int ric_transform_inv(ric_ctx *ctx, const void *arena, int16_t *plane, int stride);
+
+/* pinned host memory helpers (arenas handed to host entropy threads should be pinned) */
+int ric_host_alloc(void **p, size_t bytes);
+int ric_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
