@@ -1,0 +1,203 @@
+"""ctypes binding of librududu_b200.so, the C-ABI library declared in include/ric_b200.h.
+
+This is plumbing for the tests and bench.py: every compute call below ends in a hand-written sm_100a
+kernel.  There is no fallback: if the shared library is missing, or no CUDA device is usable,
+loading / `Context()` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librududu_b200.so")
+MAX_LEVELS = 16
+MAX_BANDS = 3 * MAX_LEVELS + 1
+
+CDF97, CDF53, HAAR = 0, 1, 2
+OK, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4
+
+EXPORTS = [
+    "ric_create", "ric_destroy", "ric_get_info", "ric_get_band", "ric_last_error", "ric_quants",
+    "ric_plane_quant", "ric_encode_u8", "ric_decode_u8", "ric_encode_u8_device", "ric_decode_u8_device",
+    "ric_last_launch_count", "ric_transform", "ric_quant", "ric_tsuq", "ric_tsuqi", "ric_transform_inv",
+    "ric_host_alloc", "ric_host_free",
+]
+
+
+class RicError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ric_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class BandInfo(C.Structure):
+    _fields_ = [("dimx", C.c_int), ("dimy", C.c_int), ("stride", C.c_int), ("is_int", C.c_int),
+                ("weight", C.c_float), ("offset", C.c_size_t)]
+
+
+class Info(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("levels", C.c_int),
+                ("level_chg", C.c_int), ("align", C.c_int), ("trans", C.c_int), ("nlev", C.c_int),
+                ("nbands", C.c_int), ("max_batch", C.c_int), ("arena_bytes", C.c_size_t),
+                ("image_arena_bytes", C.c_size_t)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library (built by __graft_entry__.build() / make -C csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.ric_create.argtypes = [C.POINTER(vp)] + [i] * 9
+        L.ric_destroy.argtypes = [vp]
+        L.ric_get_info.argtypes = [vp, C.POINTER(Info)]
+        L.ric_get_band.argtypes = [vp, i, C.POINTER(BandInfo)]
+        L.ric_last_error.restype = C.c_char_p
+        L.ric_quants.argtypes = [i]
+        L.ric_plane_quant.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+        L.ric_encode_u8.argtypes = [vp, vp, i, i, vp]
+        L.ric_decode_u8.argtypes = [vp, vp, i, i, vp]
+        L.ric_encode_u8_device.argtypes = [vp, vp, sz, i, i, vp, vp]
+        L.ric_decode_u8_device.argtypes = [vp, vp, i, i, vp, sz, vp]
+        L.ric_last_launch_count.argtypes = [vp]
+        L.ric_transform.argtypes = [vp, vp, i, vp]
+        L.ric_quant.argtypes = [vp, i, i, vp]
+        L.ric_tsuq.argtypes = [vp, i, C.c_float, vp, C.POINTER(C.c_uint)]
+        L.ric_tsuqi.argtypes = [vp, i, vp]
+        L.ric_transform_inv.argtypes = [vp, vp, vp, i]
+        L.ric_host_alloc.argtypes = [C.POINTER(vp), sz]
+        L.ric_host_free.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RicError(rc, lib().ric_last_error().decode())
+
+
+def quants(idx):
+    return lib().ric_quants(idx)
+
+
+def plane_quant(q, channels, plane):
+    a, b = C.c_int(), C.c_int()
+    _check(lib().ric_plane_quant(q, channels, plane, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def _ptr(a):
+    return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+class Context:
+    """One (width, height, channels, levels, transform) configuration on one GPU: the device-side
+    counterpart of a set of reference `CWavelet2D` objects (src/lib/wavelet2d.h:27-88)."""
+
+    def __init__(self, width, height, channels=1, levels=5, level_chg=None, align=32, trans=CDF97,
+                 max_batch=1, device=0):
+        self.L = lib()
+        if level_chg is None:
+            level_chg = max(levels - 4, 0)  # ric.cpp:159
+        h = C.c_void_p()
+        _check(self.L.ric_create(C.byref(h), device, width, height, channels, levels, level_chg, align,
+                                 trans, max_batch))
+        self.h = h
+        inf = Info()
+        _check(self.L.ric_get_info(self.h, C.byref(inf)))
+        self.info = inf
+        self.width, self.height, self.channels = width, height, channels
+        self.nlev, self.nbands = inf.nlev, inf.nbands
+        self.arena_bytes, self.image_arena_bytes = inf.arena_bytes, inf.image_arena_bytes
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ric_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def band(self, i):
+        b = BandInfo()
+        _check(self.L.ric_get_band(self.h, i, C.byref(b)))
+        return dict(dimx=b.dimx, dimy=b.dimy, stride=b.stride, is_int=b.is_int, weight=b.weight,
+                    offset=b.offset, size=4 if b.is_int else 2)
+
+    def band_view(self, arena, i, plane=0, image=0):
+        f = self.band(i)
+        dt = np.int32 if f["is_int"] else np.int16
+        o = image * self.image_arena_bytes + plane * self.arena_bytes + f["offset"]
+        return arena[o:o + f["stride"] * f["dimy"] * f["size"]].view(dt).reshape(f["dimy"], f["stride"])
+
+    # ---- whole-stage, host buffers ------------------------------------------------------------
+    def encode_u8(self, imgs, q, out=None):
+        """imgs: u8 (n, channels, height, width) -> arenas u8 (n * image_arena_bytes)."""
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8).reshape(-1, self.channels, self.height, self.width)
+        n = imgs.shape[0]
+        if out is None:
+            out = np.empty(n * self.image_arena_bytes, dtype=np.uint8)
+        _check(self.L.ric_encode_u8(self.h, _ptr(imgs), n, q, _ptr(out)))
+        return out
+
+    def decode_u8(self, arenas, n, q, out=None):
+        """arenas: signed quantised coefficients (DecodeBand output) -> u8 (n, channels, height, width)."""
+        if out is None:
+            out = np.empty((n, self.channels, self.height, self.width), dtype=np.uint8)
+        _check(self.L.ric_decode_u8(self.h, _ptr(arenas), n, q, _ptr(out)))
+        return out
+
+    # ---- device-resident variants (pointers are raw device addresses, stream a cudaStream_t) ----
+    def encode_u8_device(self, d_src, pitch, n, q, d_arenas, stream=0):
+        _check(self.L.ric_encode_u8_device(self.h, d_src, pitch, n, q, d_arenas, stream))
+
+    def decode_u8_device(self, d_arenas, n, q, d_dst, pitch, stream=0):
+        _check(self.L.ric_decode_u8_device(self.h, d_arenas, n, q, d_dst, pitch, stream))
+
+    def last_launch_count(self):
+        return self.L.ric_last_launch_count(self.h)
+
+    # ---- plane-level calls mirroring the reference class API -------------------------------------
+    def transform(self, plane):
+        """CWavelet2D::Transform<short> on one int16 plane; returns the arena of raw coefficients."""
+        p = np.ascontiguousarray(plane, dtype=np.int16)
+        a = np.empty(self.arena_bytes, dtype=np.uint8)
+        _check(self.L.ric_transform(self.h, _ptr(p), p.shape[1], _ptr(a)))
+        return a
+
+    def quant(self, Quant, lam):
+        """Quantiser half of CodeBand on the bands left on the device by transform()."""
+        a = np.empty(self.arena_bytes, dtype=np.uint8)
+        _check(self.L.ric_quant(self.h, Quant, lam, _ptr(a)))
+        return a
+
+    def tsuq(self, Quant, thres):
+        a = np.empty(self.arena_bytes, dtype=np.uint8)
+        cnt = C.c_uint()
+        _check(self.L.ric_tsuq(self.h, Quant, thres, _ptr(a), C.byref(cnt)))
+        return a, cnt.value
+
+    def tsuqi(self, arena, Quant):
+        a = np.ascontiguousarray(arena).copy()
+        _check(self.L.ric_tsuqi(self.h, Quant, _ptr(a)))
+        return a
+
+    def transform_inv(self, arena):
+        out = np.empty((self.height, self.width), dtype=np.int16)
+        a = np.ascontiguousarray(arena)
+        _check(self.L.ric_transform_inv(self.h, _ptr(a), _ptr(out), self.width))
+        return out

@@ -1,0 +1,686 @@
+// ric_b200.cu -- C ABI (include/ric_b200.h) over the sm_100a level kernels.
+//
+// There is no CPU implementation of the hot path in this library: every entry point that computes
+// launches CUDA kernels, and ric_create fails with RIC_E_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ric_fwd.cuh"
+#include "ric_host.h"
+#include "ric_inv.cuh"
+
+using namespace ric;
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+	snprintf(g_err, sizeof g_err, fmt, a, b);
+	return code;
+}
+
+#define CK(call)                                                                               \
+	do {                                                                                       \
+		cudaError_t e_ = (call);                                                               \
+		if (e_ != cudaSuccess) return set_err(RIC_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+struct ric_ctx {
+	HostGeom g;
+	int device, max_batch;
+	int sm_count;
+	cudaStream_t stream;
+	// device buffers
+	unsigned char *d_src;   // [max_batch][channels][height][src_pitch] u8
+	size_t src_pitch;
+	char *d_arena;          // [max_batch][channels][arena_bytes]  encode output (padding columns stay zero)
+	char *d_arena_in;       // same size, decode-side input (allocated on first use)
+	unsigned char *d_flags; // [max_batch][channels][flag_bytes]
+	short *d_plane;         // [channels][height][plane_pitch] s16 (plane-level API, slot 0)
+	int plane_pitch;
+	void *d_ll[RIC_MAX_LEVELS];  // LL scratch between level i and i+1: [max_batch][channels][lev_h[i+1]][ll_pitch[i]]
+	int ll_pitch[RIC_MAX_LEVELS];
+	int ll_es[RIC_MAX_LEVELS];
+	unsigned *d_count;
+	int launches;
+	int target_warps;
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel dispatch tables
+
+typedef void (*fwd_fn)(const FwdParams);
+typedef void (*inv_fn)(const InvParams);
+
+template <bool SH, int TRANS>
+static fwd_fn pick_fwd2(int src, int lldst)
+{
+	if (SH) {
+		if (src == SRC_U8_GRAY) return lldst == LL_BAND ? fwd_level_kernel<true, TRANS, SRC_U8_GRAY, LL_BAND> : fwd_level_kernel<true, TRANS, SRC_U8_GRAY, LL_S16>;
+		if (src == SRC_U8_RGB) return lldst == LL_BAND ? fwd_level_kernel<true, TRANS, SRC_U8_RGB, LL_BAND> : fwd_level_kernel<true, TRANS, SRC_U8_RGB, LL_S16>;
+		if (src == SRC_S16) return lldst == LL_BAND ? fwd_level_kernel<true, TRANS, SRC_S16, LL_BAND> : fwd_level_kernel<true, TRANS, SRC_S16, LL_S16>;
+		return nullptr;
+	}
+	if (src == SRC_S16) return lldst == LL_BAND ? fwd_level_kernel<false, TRANS, SRC_S16, LL_BAND> : fwd_level_kernel<false, TRANS, SRC_S16, LL_S32>;
+	if (src == SRC_S32) return lldst == LL_BAND ? fwd_level_kernel<false, TRANS, SRC_S32, LL_BAND> : fwd_level_kernel<false, TRANS, SRC_S32, LL_S32>;
+	return nullptr;
+}
+
+static fwd_fn pick_fwd(bool sh, int trans, int src, int lldst)
+{
+	if (trans == RIC_CDF97) return sh ? pick_fwd2<true, T97>(src, lldst) : pick_fwd2<false, T97>(src, lldst);
+	return sh ? pick_fwd2<true, T53>(src, lldst) : pick_fwd2<false, T53>(src, lldst);
+}
+
+template <bool SH, int TRANS>
+static inv_fn pick_inv2(int llsrc, int dst)
+{
+	if (SH) {
+#define RIC_ROW(LS)                                                                        \
+	if (llsrc == LS) {                                                                     \
+		if (dst == DST_S16) return inv_level_kernel<true, TRANS, LS, DST_S16>;             \
+		if (dst == DST_U8_GRAY) return inv_level_kernel<true, TRANS, LS, DST_U8_GRAY>;     \
+		if (dst == DST_U8_RGB) return inv_level_kernel<true, TRANS, LS, DST_U8_RGB>;       \
+	}
+		RIC_ROW(LLSRC_S16)
+		RIC_ROW(LLSRC_S32)
+		RIC_ROW(LLSRC_BAND)
+#undef RIC_ROW
+		return nullptr;
+	}
+	if (dst != DST_S32) return nullptr;
+	if (llsrc == LLSRC_S32) return inv_level_kernel<false, TRANS, LLSRC_S32, DST_S32>;
+	if (llsrc == LLSRC_BAND) return inv_level_kernel<false, TRANS, LLSRC_BAND, DST_S32>;
+	return nullptr;
+}
+
+static inv_fn pick_inv(bool sh, int trans, int llsrc, int dst)
+{
+	if (trans == RIC_CDF97) return sh ? pick_inv2<true, T97>(llsrc, dst) : pick_inv2<false, T97>(llsrc, dst);
+	return sh ? pick_inv2<true, T53>(llsrc, dst) : pick_inv2<false, T53>(llsrc, dst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone kernels behind the class-level API (CBandCodec::buildTree on resident bands,
+// CWavelet2D::TSUQ / TSUQi on all bands)
+
+struct QuantLevelParams {
+	char *arena;
+	unsigned char *flags;
+	BandRef band[3], child[3];
+	int has_child, is_int;
+	QuantBand qb[3];
+};
+
+template <bool SH>
+__global__ void quant_level_kernel(const __grid_constant__ QuantLevelParams P)
+{
+	__shared__ QuantBand s_qb[3];
+	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
+	__syncthreads();
+	const int o = blockIdx.y;
+	const BandRef &b = P.band[o];
+	const int nbx = b.fl_bw, nby = (b.dimy + 3) / 4;
+	const int id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= nbx * nby) return;
+	const int bx = id % nbx, by = id / nbx;
+	const int bw = min(4, b.dimx - 4 * bx), bh = min(4, b.dimy - 4 * by);
+	constexpr int ES = SH ? 2 : 4;
+	char *base = P.arena + b.off;
+	int c[16];
+#pragma unroll
+	for (int k = 0; k < 16; k++) {
+		const int r = k >> 2, x = k & 3;
+		c[k] = 0;
+		if (r < bh && x < bw) {
+			const char *p = base + ((long long)(4 * by + r) * b.stride + 4 * bx + x) * ES;
+			c[k] = SH ? (int)*(const short *)p : *(const int *)p;
+		}
+	}
+	int nz = quant_block<SH>(c, &s_qb[o], bw, bh);
+	if (P.has_child && bw == 4 && bh == 4) {
+		const BandRef &ch = P.child[o];
+		const unsigned char *cf = P.flags + ch.fl_off + (2 * by) * ch.fl_bw + 2 * bx;
+		nz += cf[0] + cf[1] + cf[ch.fl_bw] + cf[ch.fl_bw + 1];
+	}
+	P.flags[b.fl_off + by * b.fl_bw + bx] = nz != 0;
+	if (nz == 0) c[0] = -0x8000;
+#pragma unroll
+	for (int k = 0; k < 16; k++) {
+		const int r = k >> 2, x = k & 3;
+		if (r < bh && x < bw) {
+			char *p = base + ((long long)(4 * by + r) * b.stride + 4 * bx + x) * ES;
+			if (SH) *(short *)p = (short)c[k]; else *(int *)p = c[k];
+		}
+	}
+}
+
+// mode 0: TSUQ (dead-zone quantise, count non-zeros); mode 1: TSUQi (multiply)
+template <bool SH>
+__global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int dimy, int stride, int mode, int Q,
+                                      int iQ, int T, unsigned *count)
+{
+	const long long n = (long long)dimx * dimy;
+	unsigned local = 0;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const int y = (int)(i / dimx), x = (int)(i % dimx);
+		char *p = arena + off + ((long long)y * stride + x) * (SH ? 2 : 4);
+		int c = SH ? (int)*(short *)p : *(int *)p;
+		if (mode == 0) {
+			// Count counts every coefficient outside the dead zone (band.h:77-80), even if it rounds to 0
+			local += !((unsigned)(c + T) <= (unsigned)(2 * T));
+			c = tsuq1<SH>(c, T, iQ);
+		} else {
+			c = TR<SH>(c * Q);
+		}
+		if (SH) *(short *)p = (short)c; else *(int *)p = c;
+	}
+	if (mode == 0 && count) {
+		local = __reduce_add_sync(0xffffffffu, local);
+		if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static BandRef band_ref(const HostGeom &g, int id)
+{
+	BandRef r;
+	const ric_band_info &b = g.band[id];
+	r.off = (long long)b.offset;
+	r.dimx = b.dimx; r.dimy = b.dimy; r.stride = b.stride;
+	r.fl_off = g.flag_off[id];
+	r.fl_bw = g.flag_bw[id];
+	return r;
+}
+
+static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_images)
+{
+	const int nstrips = (w + STRIP_W - 1) / STRIP_W;
+	int seg = 128;
+	while (seg > 16) {
+		const long long jobs = (long long)nstrips * ((h + seg - 1) / seg) * planes_images;
+		if (jobs >= c->target_warps) break;
+		seg >>= 1;
+	}
+	return seg;
+}
+
+extern "C" {
+
+const char *ric_last_error(void) { return g_err; }
+int ric_quants(int idx) { return quants(idx); }
+
+int ric_plane_quant(int q, int channels, int plane, int *Quant, int *lambda)
+{
+	if (q < 0 || q > 31 || (channels != 1 && channels != 3) || plane < 0 || plane >= channels || !Quant || !lambda)
+		return set_err(RIC_E_ARG, "ric_plane_quant: bad argument");
+	plane_quant(q, channels, plane, Quant, lambda);
+	return RIC_OK;
+}
+
+int ric_destroy(ric_ctx *c)
+{
+	if (!c) return RIC_OK;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	cudaFree(c->d_src);
+	cudaFree(c->d_arena);
+	cudaFree(c->d_arena_in);
+	cudaFree(c->d_flags);
+	cudaFree(c->d_plane);
+	cudaFree(c->d_count);
+	for (int i = 0; i < RIC_MAX_LEVELS; i++) cudaFree(c->d_ll[i]);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+	return RIC_OK;
+}
+
+int ric_create(ric_ctx **out, int device, int width, int height, int channels, int levels, int level_chg, int align,
+               int trans, int max_batch)
+{
+	if (!out || max_batch < 1) return set_err(RIC_E_ARG, "ric_create: bad argument");
+	*out = nullptr;
+	HostGeom g;
+	int rc = geom_init(g, width, height, channels, levels, level_chg, align, trans);
+	if (rc != RIC_OK) return set_err(rc, "ric_create: unsupported geometry/transform");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return set_err(RIC_E_CUDA, "ric_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+	if (device < 0 || device >= ndev) return set_err(RIC_E_ARG, "ric_create: bad device index");
+	CK(cudaSetDevice(device));
+	ric_ctx *c = new (std::nothrow) ric_ctx();
+	if (!c) return set_err(RIC_E_NOMEM, "ric_create: out of host memory");
+	memset(c, 0, sizeof *c);
+	c->g = g;
+	c->device = device;
+	c->max_batch = max_batch;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	c->sm_count = prop.multiProcessorCount;
+	const char *tw = getenv("RIC_TARGET_WARPS");
+	c->target_warps = tw ? atoi(tw) : c->sm_count * 16;
+#define CKD(call)                                                                    \
+	do {                                                                             \
+		cudaError_t e_ = (call);                                                     \
+		if (e_ != cudaSuccess) {                                                     \
+			set_err(e_ == cudaErrorMemoryAllocation ? RIC_E_NOMEM : RIC_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+			ric_destroy(c);                                                          \
+			return e_ == cudaErrorMemoryAllocation ? RIC_E_NOMEM : RIC_E_CUDA;       \
+		}                                                                            \
+	} while (0)
+	CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	const size_t nb = (size_t)max_batch, ch = (size_t)channels;
+	c->src_pitch = ((size_t)width + 7 + 8) & ~(size_t)7;  // >= roundup8(w), one spare vector
+	CKD(cudaMalloc(&c->d_src, nb * ch * height * c->src_pitch + 64));
+	CKD(cudaMalloc(&c->d_arena, nb * ch * g.arena_bytes + 64));
+	CKD(cudaMemset(c->d_arena, 0, nb * ch * g.arena_bytes + 64));  // padding columns stay zero
+	CKD(cudaMalloc(&c->d_flags, nb * ch * g.flag_bytes));
+	CKD(cudaMemset(c->d_flags, 0, nb * ch * g.flag_bytes));
+	c->plane_pitch = (width + 7 + 8) & ~7;
+	CKD(cudaMalloc(&c->d_plane, ch * height * (size_t)c->plane_pitch * sizeof(short) + 64));
+	for (int i = 0; i + 1 < g.nlev; i++) {
+		c->ll_pitch[i] = (g.lev_w[i + 1] + 7 + 8) & ~7;
+		c->ll_es[i] = (g.lev_int[i] || g.lev_int[i + 1]) ? 4 : 2;
+		const size_t bytes = nb * ch * g.lev_h[i + 1] * (size_t)c->ll_pitch[i] * c->ll_es[i] + 64;
+		CKD(cudaMalloc(&c->d_ll[i], bytes));
+		CKD(cudaMemset(c->d_ll[i], 0, bytes));
+	}
+	CKD(cudaMalloc(&c->d_count, sizeof(unsigned)));
+	CKD(cudaDeviceSynchronize());
+#undef CKD
+	*out = c;
+	return RIC_OK;
+}
+
+int ric_get_info(const ric_ctx *c, ric_info *info)
+{
+	if (!c || !info) return set_err(RIC_E_ARG, "ric_get_info: null");
+	const HostGeom &g = c->g;
+	info->width = g.width; info->height = g.height; info->channels = g.channels;
+	info->levels = g.levels; info->level_chg = g.level_chg; info->align = g.align; info->trans = g.trans;
+	info->nlev = g.nlev; info->nbands = g.nbands; info->max_batch = c->max_batch;
+	info->arena_bytes = g.arena_bytes;
+	info->image_arena_bytes = g.arena_bytes * g.channels;
+	return RIC_OK;
+}
+
+int ric_get_band(const ric_ctx *c, int id, ric_band_info *info)
+{
+	if (!c || !info || id < 0 || id >= c->g.nbands) return set_err(RIC_E_ARG, "ric_get_band: bad argument");
+	*info = c->g.band[id];
+	return RIC_OK;
+}
+
+int ric_last_launch_count(const ric_ctx *c) { return c ? c->launches : 0; }
+
+int ric_host_alloc(void **p, size_t bytes)
+{
+	if (!p) return set_err(RIC_E_ARG, "ric_host_alloc: null");
+	cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+	if (e != cudaSuccess) return set_err(RIC_E_NOMEM, "cudaHostAlloc: %s", cudaGetErrorString(e));
+	return RIC_OK;
+}
+
+int ric_host_free(void *p)
+{
+	if (p) cudaFreeHost(p);
+	return RIC_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// launch sequences
+
+// Forward: all levels of n images.  src_kind SRC_U8_* (d_src, pitch bytes) or SRC_S16 (plane API).
+// Quant[p]/lambda[p] per plane; do_quant = 0 stores raw coefficients.
+static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long src_img_stride,
+                          long long src_plane_stride, int src_pitch, int n, int nplanes, int shift, int do_quant,
+                          const int *Quant, const int *lambda, char *d_arena, cudaStream_t st)
+{
+	const HostGeom &g = c->g;
+	c->launches = 0;
+	for (int lv = 0; lv < g.nlev; lv++) {
+		FwdParams P;
+		memset(&P, 0, sizeof P);
+		const bool last = lv == g.nlev - 1;
+		const bool sh = !g.lev_int[lv];
+		int src, lldst;
+		if (lv == 0) {
+			P.src = d_src; src = src_kind;
+			P.src_img_stride = src_img_stride; P.src_plane_stride = src_plane_stride; P.src_pitch = src_pitch;
+		} else {
+			P.src = c->d_ll[lv - 1];
+			src = c->ll_es[lv - 1] == 4 && g.lev_int[lv - 1] ? SRC_S32 : SRC_S16;
+			P.src_pitch = c->ll_pitch[lv - 1];
+			P.src_plane_stride = (long long)g.lev_h[lv] * P.src_pitch;
+			P.src_img_stride = P.src_plane_stride * g.channels;
+		}
+		if (last) lldst = LL_BAND;
+		else {
+			lldst = g.lev_int[lv] ? LL_S32 : LL_S16;
+			P.ll = c->d_ll[lv];
+			P.ll_pitch = c->ll_pitch[lv];
+			P.ll_plane_stride = (long long)g.lev_h[lv + 1] * P.ll_pitch;
+			P.ll_img_stride = P.ll_plane_stride * g.channels;
+		}
+		P.arena = d_arena;
+		P.arena_plane_stride = (long long)g.arena_bytes;
+		P.arena_img_stride = (long long)g.arena_bytes * g.channels;
+		P.flags = c->d_flags;
+		P.flags_plane_stride = (long long)g.flag_bytes;
+		P.flags_img_stride = (long long)g.flag_bytes * g.channels;
+		for (int o = 0; o < 3; o++) {
+			P.band[o] = band_ref(g, 3 * lv + o);
+			if (lv > 0) P.child[o] = band_ref(g, 3 * (lv - 1) + o);
+		}
+		P.lband = band_ref(g, 3 * g.nlev);
+		P.has_child = lv > 0;
+		P.w = g.lev_w[lv]; P.h = g.lev_h[lv];
+		P.nstrips = (P.w + STRIP_W - 1) / STRIP_W;
+		P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)nplanes * n);
+		P.nsegs = (P.h + P.seg_rows - 1) / P.seg_rows;
+		P.nplanes = nplanes; P.nimages = n;
+		P.shift = shift; P.quant = do_quant;
+		// quantiser classes: plane 2 of an RGB image is luma (class 0), planes 0/1 chroma (class 1)
+		int cls_plane[2] = {nplanes == 3 ? 2 : 0, 0};
+		for (int p = 0; p < 3; p++) P.plane_class[p] = (nplanes == 3 && p != 2) ? 1 : 0;
+		if (do_quant) {
+			for (int cls = 0; cls < 2; cls++) {
+				const int p = cls_plane[cls];
+				for (int o = 0; o < 3; o++) {
+					HostQuantBand hq;
+					make_quant_band(hq, Quant[p], lambda[p], g.band[3 * lv + o].weight, g.lev_int[lv]);
+					QuantBand &q = P.qb[cls][o];
+					q.Q = hq.Q; q.iQ = hq.iQ; q.T = hq.T; q.Te = hq.Te;
+					for (int i = 0; i < 16; i++) q.thr[i] = hq.thr[i];
+				}
+				make_tsuq(Quant[p], 0.5f, g.band[3 * g.nlev].weight, g.lev_int[g.nlev - 1], &P.llQ[cls], &P.lliQ[cls], &P.llT[cls]);
+			}
+		}
+		fwd_fn fn = pick_fwd(sh, g.trans, src, lldst);
+		if (!fn) return set_err(RIC_E_UNSUPPORTED, "forward: unsupported level type combination");
+		const long long njobs = (long long)P.nstrips * P.nsegs * nplanes * n;
+		const int wpb = 4;
+		const unsigned grid = (unsigned)((njobs + wpb - 1) / wpb);
+		fn<<<grid, wpb * 32, 0, st>>>(P);
+		CK(cudaGetLastError());
+		c->launches++;
+	}
+	return RIC_OK;
+}
+
+// Inverse: all levels of n images.  dq_Quant[p] = TSUQi argument per plane (0: no dequantisation).
+static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, int shift, const int *dq_Quant,
+                          int dst_kind, void *d_dst, long long dst_img_stride, long long dst_plane_stride,
+                          int dst_pitch, int q1_quirk, cudaStream_t st)
+{
+	const HostGeom &g = c->g;
+	c->launches = 0;
+	for (int lv = g.nlev - 1; lv >= 0; lv--) {
+		InvParams P;
+		memset(&P, 0, sizeof P);
+		const bool coarsest = lv == g.nlev - 1;
+		const bool sh = !g.lev_int[lv];
+		P.arena = d_arena;
+		P.arena_plane_stride = (long long)g.arena_bytes;
+		P.arena_img_stride = (long long)g.arena_bytes * g.channels;
+		int llsrc, dst;
+		if (coarsest) llsrc = LLSRC_BAND;
+		else {
+			llsrc = g.lev_int[lv + 1] ? LLSRC_S32 : LLSRC_S16;
+			P.ll = c->d_ll[lv];
+			P.ll_pitch = c->ll_pitch[lv];
+			P.ll_plane_stride = (long long)g.lev_h[lv + 1] * P.ll_pitch;
+			P.ll_img_stride = P.ll_plane_stride * g.channels;
+		}
+		if (lv == 0) {
+			dst = dst_kind;
+			P.dst = d_dst; P.dst_img_stride = dst_img_stride; P.dst_plane_stride = dst_plane_stride; P.dst_pitch = dst_pitch;
+		} else {
+			dst = g.lev_int[lv] ? DST_S32 : DST_S16;
+			P.dst = c->d_ll[lv - 1];
+			P.dst_pitch = c->ll_pitch[lv - 1];
+			P.dst_plane_stride = (long long)g.lev_h[lv] * P.dst_pitch;
+			P.dst_img_stride = P.dst_plane_stride * g.channels;
+		}
+		for (int o = 0; o < 3; o++) P.band[o] = band_ref(g, 3 * lv + o);
+		P.lband = band_ref(g, 3 * g.nlev);
+		P.h_row1_off = (g.trans == RIC_CDF53 && q1_quirk) ? P.band[0].stride : P.band[1].stride;
+		P.w = g.lev_w[lv]; P.h = g.lev_h[lv];
+		P.nstrips = (P.w + STRIP_W - 1) / STRIP_W;
+		const int jplanes = dst == DST_U8_RGB ? 1 : nplanes;
+		P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)jplanes * n);
+		P.nsegs = (P.h + P.seg_rows - 1) / P.seg_rows;
+		P.nplanes = nplanes; P.nimages = n;
+		P.shift = shift;
+		for (int p = 0; p < 3; p++)
+			for (int o = 0; o < 4; o++) {
+				const int id = o < 3 ? 3 * lv + o : 3 * g.nlev;
+				P.dq[p][o] = (p < nplanes && dq_Quant[p]) ? make_tsuqi(dq_Quant[p], g.band[id].weight, g.band[id].is_int) : 1;
+			}
+		inv_fn fn = pick_inv(sh, g.trans, llsrc, dst);
+		if (!fn) return set_err(RIC_E_UNSUPPORTED, "inverse: unsupported level type combination");
+		const long long njobs = (long long)P.nstrips * P.nsegs * jplanes * n;
+		const int wpb = 4;
+		const unsigned grid = (unsigned)((njobs + wpb - 1) / wpb);
+		fn<<<grid, wpb * 32, 0, st>>>(P);
+		CK(cudaGetLastError());
+		c->launches++;
+	}
+	return RIC_OK;
+}
+
+static int need_arena_in(ric_ctx *c)
+{
+	if (c->d_arena_in) return RIC_OK;
+	const size_t bytes = (size_t)c->max_batch * c->g.channels * c->g.arena_bytes + 64;
+	cudaError_t e = cudaMalloc(&c->d_arena_in, bytes);
+	if (e != cudaSuccess) return set_err(RIC_E_NOMEM, "cudaMalloc(decode arena): %s", cudaGetErrorString(e));
+	return RIC_OK;
+}
+
+static int check_batch(const ric_ctx *c, int n, int q, const char *who)
+{
+	if (!c) return set_err(RIC_E_ARG, "%s: null context", who);
+	if (n < 1 || n > c->max_batch) return set_err(RIC_E_ARG, "%s: batch size outside [1, max_batch]", who);
+	if (q < 0 || q > 31) return set_err(RIC_E_ARG, "%s: q outside [0, 31]", who);
+	return RIC_OK;
+}
+
+extern "C" {
+
+int ric_encode_u8_device(ric_ctx *c, const uint8_t *d_src, size_t pitch, int n, int q, void *d_arenas, void *stream)
+{
+	int rc = check_batch(c, n, q, "ric_encode_u8_device");
+	if (rc) return rc;
+	const HostGeom &g = c->g;
+	if (!d_src || !d_arenas || (pitch & 7) || pitch < (size_t)((g.width + 7) & ~7) || ((uintptr_t)d_src & 7) ||
+	    ((uintptr_t)d_arenas & 31))
+		return set_err(RIC_E_ARG, "ric_encode_u8_device: bad pointer/pitch (pitch must be a multiple of 8 and >= roundup8(width))");
+	CK(cudaSetDevice(c->device));
+	int Q[3] = {0, 0, 0}, L[3] = {0, 0, 0};
+	for (int p = 0; p < g.channels; p++) plane_quant(q, g.channels, p, &Q[p], &L[p]);
+	return launch_forward(c, d_src, g.channels == 3 ? SRC_U8_RGB : SRC_U8_GRAY, (long long)pitch * g.height * g.channels,
+	                      (long long)pitch * g.height, (int)pitch, n, g.channels, q != 0, 1, Q, L, (char *)d_arenas,
+	                      (cudaStream_t)stream);
+}
+
+int ric_decode_u8_device(ric_ctx *c, const void *d_arenas, int n, int q, uint8_t *d_dst, size_t pitch, void *stream)
+{
+	int rc = check_batch(c, n, q, "ric_decode_u8_device");
+	if (rc) return rc;
+	const HostGeom &g = c->g;
+	if (!d_dst || !d_arenas || (pitch & 7) || pitch < (size_t)((g.width + 7) & ~7) || ((uintptr_t)d_dst & 7) ||
+	    ((uintptr_t)d_arenas & 31))
+		return set_err(RIC_E_ARG, "ric_decode_u8_device: bad pointer/pitch (pitch must be a multiple of 8 and >= roundup8(width))");
+	CK(cudaSetDevice(c->device));
+	int Q[3] = {0, 0, 0}, L[3];
+	for (int p = 0; p < g.channels; p++) plane_quant(q, g.channels, p, &Q[p], &L[p]);
+	return launch_inverse(c, (const char *)d_arenas, n, g.channels, q != 0, Q, g.channels == 3 ? DST_U8_RGB : DST_U8_GRAY,
+	                      d_dst, (long long)pitch * g.height * g.channels, (long long)pitch * g.height, (int)pitch, 1,
+	                      (cudaStream_t)stream);
+}
+
+int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
+{
+	int rc = check_batch(c, n, q, "ric_encode_u8");
+	if (rc) return rc;
+	if (!src || !arenas) return set_err(RIC_E_ARG, "ric_encode_u8: null buffer");
+	const HostGeom &g = c->g;
+	CK(cudaSetDevice(c->device));
+	const size_t rows = (size_t)n * g.channels * g.height;
+	CK(cudaMemcpy2DAsync(c->d_src, c->src_pitch, src, g.width, g.width, rows, cudaMemcpyHostToDevice, c->stream));
+	rc = ric_encode_u8_device(c, c->d_src, c->src_pitch, n, q, c->d_arena, c->stream);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(arenas, c->d_arena, (size_t)n * g.channels * g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+int ric_decode_u8(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst)
+{
+	int rc = check_batch(c, n, q, "ric_decode_u8");
+	if (rc) return rc;
+	if (!dst || !arenas) return set_err(RIC_E_ARG, "ric_decode_u8: null buffer");
+	const HostGeom &g = c->g;
+	CK(cudaSetDevice(c->device));
+	if ((rc = need_arena_in(c))) return rc;
+	CK(cudaMemcpyAsync(c->d_arena_in, arenas, (size_t)n * g.channels * g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
+	rc = ric_decode_u8_device(c, c->d_arena_in, n, q, c->d_src, c->src_pitch, c->stream);
+	if (rc) return rc;
+	const size_t rows = (size_t)n * g.channels * g.height;
+	CK(cudaMemcpy2DAsync(dst, g.width, c->d_src, c->src_pitch, g.width, rows, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+// ---- plane-level API (one plane, batch slot 0, plane slot 0) ------------------------------------
+
+int ric_transform(ric_ctx *c, const int16_t *plane, int stride, void *arena)
+{
+	if (!c || !plane) return set_err(RIC_E_ARG, "ric_transform: null");
+	const HostGeom &g = c->g;
+	if (stride < g.width) return set_err(RIC_E_ARG, "ric_transform: stride < width");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpy2DAsync(c->d_plane, (size_t)c->plane_pitch * 2, plane, (size_t)stride * 2, (size_t)g.width * 2, g.height,
+	                     cudaMemcpyHostToDevice, c->stream));
+	int Q[3] = {0, 0, 0};
+	int rc = launch_forward(c, c->d_plane, SRC_S16, 0, 0, c->plane_pitch, 1, 1, 0, 0, Q, Q, c->d_arena, c->stream);
+	if (rc) return rc;
+	if (arena) CK(cudaMemcpyAsync(arena, c->d_arena, g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+int ric_quant(ric_ctx *c, int Quant, int lambda, void *arena)
+{
+	if (!c || Quant < 0 || lambda < 0) return set_err(RIC_E_ARG, "ric_quant: bad argument");
+	const HostGeom &g = c->g;
+	CK(cudaSetDevice(c->device));
+	for (int lv = 0; lv < g.nlev; lv++) {
+		QuantLevelParams P;
+		memset(&P, 0, sizeof P);
+		P.arena = c->d_arena;
+		P.flags = c->d_flags;
+		P.has_child = lv > 0;
+		P.is_int = g.lev_int[lv];
+		int maxblk = 0;
+		for (int o = 0; o < 3; o++) {
+			P.band[o] = band_ref(g, 3 * lv + o);
+			if (lv > 0) P.child[o] = band_ref(g, 3 * (lv - 1) + o);
+			HostQuantBand hq;
+			make_quant_band(hq, Quant, lambda, g.band[3 * lv + o].weight, g.lev_int[lv]);
+			QuantBand &q = P.qb[o];
+			q.Q = hq.Q; q.iQ = hq.iQ; q.T = hq.T; q.Te = hq.Te;
+			for (int i = 0; i < 16; i++) q.thr[i] = hq.thr[i];
+			maxblk = std::max(maxblk, P.band[o].fl_bw * ((P.band[o].dimy + 3) / 4));
+		}
+		dim3 grid((maxblk + 127) / 128, 3);
+		if (g.lev_int[lv]) quant_level_kernel<false><<<grid, 128, 0, c->stream>>>(P);
+		else quant_level_kernel<true><<<grid, 128, 0, c->stream>>>(P);
+		CK(cudaGetLastError());
+	}
+	{
+		const ric_band_info &b = g.band[3 * g.nlev];
+		int Q, iQ, T;
+		make_tsuq(Quant, 0.5f, b.weight, b.is_int, &Q, &iQ, &T);
+		if (b.is_int) band_pointwise_kernel<false><<<32, 128, 0, c->stream>>>(c->d_arena, (long long)b.offset, b.dimx, b.dimy, b.stride, 0, Q, iQ, T, nullptr);
+		else band_pointwise_kernel<true><<<32, 128, 0, c->stream>>>(c->d_arena, (long long)b.offset, b.dimx, b.dimy, b.stride, 0, Q, iQ, T, nullptr);
+		CK(cudaGetLastError());
+	}
+	if (arena) CK(cudaMemcpyAsync(arena, c->d_arena, g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+static int pointwise_all(ric_ctx *c, char *d_arena, int mode, int Quant, float thres, unsigned *count)
+{
+	const HostGeom &g = c->g;
+	CK(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
+	for (int id = 0; id < g.nbands; id++) {
+		const ric_band_info &b = g.band[id];
+		int Q = 1, iQ = 0, T = 0;
+		if (mode == 0) make_tsuq(Quant, id == 3 * g.nlev ? 0.5f : thres, b.weight, b.is_int, &Q, &iQ, &T);  // LL: wavelet2d.cpp:240-243
+		else Q = make_tsuqi(Quant, b.weight, b.is_int);
+		const int blocks = std::max(1, std::min(1024, (b.dimx * b.dimy + 1023) / 1024));
+		if (b.is_int) band_pointwise_kernel<false><<<blocks, 256, 0, c->stream>>>(d_arena, (long long)b.offset, b.dimx, b.dimy, b.stride, mode, Q, iQ, T, c->d_count);
+		else band_pointwise_kernel<true><<<blocks, 256, 0, c->stream>>>(d_arena, (long long)b.offset, b.dimx, b.dimy, b.stride, mode, Q, iQ, T, c->d_count);
+		CK(cudaGetLastError());
+	}
+	if (count) CK(cudaMemcpyAsync(count, c->d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+	return RIC_OK;
+}
+
+int ric_tsuq(ric_ctx *c, int Quant, float thres, void *arena, unsigned *count)
+{
+	if (!c || Quant < 0) return set_err(RIC_E_ARG, "ric_tsuq: bad argument");
+	CK(cudaSetDevice(c->device));
+	int rc = pointwise_all(c, c->d_arena, 0, Quant, thres, count);
+	if (rc) return rc;
+	if (arena) CK(cudaMemcpyAsync(arena, c->d_arena, c->g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+int ric_tsuqi(ric_ctx *c, int Quant, void *arena)
+{
+	if (!c || !arena || Quant < 0) return set_err(RIC_E_ARG, "ric_tsuqi: bad argument");
+	CK(cudaSetDevice(c->device));
+	int rc = need_arena_in(c);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(c->d_arena_in, arena, c->g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
+	rc = pointwise_all(c, c->d_arena_in, 1, Quant, 0.f, nullptr);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(arena, c->d_arena_in, c->g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+int ric_transform_inv(ric_ctx *c, const void *arena, int16_t *plane, int stride)
+{
+	if (!c || !arena || !plane) return set_err(RIC_E_ARG, "ric_transform_inv: null");
+	const HostGeom &g = c->g;
+	if (stride < g.width) return set_err(RIC_E_ARG, "ric_transform_inv: stride < width");
+	CK(cudaSetDevice(c->device));
+	int rc = need_arena_in(c);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(c->d_arena_in, arena, g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
+	int Q[3] = {0, 0, 0};
+	rc = launch_inverse(c, c->d_arena_in, 1, 1, 0, Q, DST_S16, c->d_plane, 0, 0, c->plane_pitch, 1, c->stream);
+	if (rc) return rc;
+	CK(cudaMemcpy2DAsync(plane, (size_t)stride * 2, c->d_plane, (size_t)c->plane_pitch * 2, (size_t)g.width * 2, g.height,
+	                     cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+}  // extern "C"

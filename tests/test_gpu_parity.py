@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path (through the C ABI, via ctypes) against the oracle on the same inputs.
+
+Bit-exact (integer path): every comparison is array_equal / CRC equality, tolerance 0.
+The oracle (oracle/ric_oracle.c) is itself pinned against the compiled reference by
+tests/test_oracle_vs_ref.py; tests/golden/kats.json holds reference-generated CRCs for the
+BASELINE.json shapes.
+"""
+import numpy as np
+import pytest
+
+import oraclebind
+from refutil import crc
+from rududu_image_codec_b200 import capi
+from rududu_image_codec_b200.synth import synth_image
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(512, 512), (517, 389), (64, 48), (33, 47), (250, 131), (16, 16), (129, 130), (96, 17), (241, 64),
+          (480, 270), (1000, 40)]
+CFGS = [(5, 1, 0), (5, 0, 0), (6, 2, 0), (4, 3, 0), (5, 1, 1), (5, 0, 1)]
+
+
+def _diff(o, a, b, nplanes=1):
+    for p in range(nplanes):
+        for i in range(o.nbands):
+            f = o.info(i)
+            x = o.band_view(a, i, p)[:, :f["dimx"]]
+            y = o.band_view(b, i, p)[:, :f["dimx"]]
+            if not np.array_equal(x, y):
+                bad = np.argwhere(x != y)
+                return "plane %d band %d (%dx%d): %d diffs, first at %s: got %d want %d" % (
+                    p, i, f["dimx"], f["dimy"], len(bad), bad[0], x[tuple(bad[0])], y[tuple(bad[0])])
+    return None
+
+
+@pytest.mark.parametrize("w,h", SHAPES)
+@pytest.mark.parametrize("levels,chg,trans", CFGS)
+def test_transform_full_range(w, h, levels, chg, trans):
+    rng = np.random.default_rng(w * 7919 + h + levels + 10 * trans)
+    plane = rng.integers(-32768, 32768, size=(h, w), dtype=np.int16)
+    o = oraclebind.Oracle(w, h, levels, chg, trans=trans)
+    with capi.Context(w, h, 1, levels, chg, trans=trans) as c:
+        assert c.arena_bytes == o.arena_bytes
+        for i in range(o.nbands):
+            f, g = o.info(i), c.band(i)
+            assert f == g
+        got = c.transform(plane)
+    assert _diff(o, got, o.forward(plane)) is None
+
+
+@pytest.mark.parametrize("w,h", SHAPES)
+@pytest.mark.parametrize("levels,chg,trans", [(5, 1, 0), (5, 0, 0), (6, 2, 0), (5, 1, 1)])
+def test_transform_inv_full_range(w, h, levels, chg, trans):
+    rng = np.random.default_rng(w * 31 + h + levels)
+    o = oraclebind.Oracle(w, h, levels, chg, trans=trans)
+    a = o.new_arena()
+    for i in range(o.nbands):
+        f = o.info(i)
+        lo, hi = (-2 ** 20, 2 ** 20) if f["is_int"] else (-32768, 32768)
+        o.band_view(a, i)[:, :f["dimx"]] = rng.integers(lo, hi, size=(f["dimy"], f["dimx"]))
+    with capi.Context(w, h, 1, levels, chg, trans=trans) as c:
+        got = c.transform_inv(a)
+    assert np.array_equal(got, o.inverse(a, q1_quirk=1))
+
+
+@pytest.mark.parametrize("Quant,lam", [(7, 3), (96, 36), (1000, 400), (6144, 3000), (30000, 12000)])
+@pytest.mark.parametrize("w,h", [(203, 151), (512, 256)])
+def test_quant_random_coefficients(Quant, lam, w, h):
+    """Heavy-tailed planes: ties in the candidate ranking, every rank threshold, partial blocks,
+    int32 coarse levels, and (large Quant) the int16 wrap paths."""
+    rng = np.random.default_rng(Quant)
+    plane = (rng.standard_cauchy(size=(h, w)) * Quant / 6).clip(-32768, 32767).astype(np.int16)
+    o = oraclebind.Oracle(w, h, 5, 1)
+    want = o.forward(plane)
+    o.quant(want, Quant, lam)
+    with capi.Context(w, h, 1, 5, 1) as c:
+        c.transform(plane)
+        got = c.quant(Quant, lam)
+    assert _diff(o, got, want) is None
+
+
+def test_tsuq_and_tsuqi():
+    w, h = 250, 131
+    rng = np.random.default_rng(5)
+    plane = rng.integers(-3000, 3000, size=(h, w), dtype=np.int16)
+    o = oraclebind.Oracle(w, h, 5, 1)
+    want = o.forward(plane)
+    cnt = o.tsuq_all(want, 96, 0.7)
+    with capi.Context(w, h, 1, 5, 1) as c:
+        c.transform(plane)
+        got, gcnt = c.tsuq(96, 0.7)
+        assert gcnt == cnt
+        assert _diff(o, got, want) is None
+        o.tsuqi(want, 96)
+        assert _diff(o, c.tsuqi(got, 96), want) is None
+
+
+@pytest.mark.parametrize("w,h", [(512, 512), (517, 389), (250, 131), (33, 47), (129, 130), (1920, 1080)])
+@pytest.mark.parametrize("q", [0, 1, 4, 9, 16, 31])
+@pytest.mark.parametrize("ch", [1, 3])
+def test_encode_stage(w, h, q, ch):
+    img = synth_image(3, w, h, ch)
+    trans = 1 if q == 0 else 0
+    o = oraclebind.Oracle(w, h, 5, trans=trans)
+    want = o.encode_image(img, q)
+    with capi.Context(w, h, ch, 5, trans=trans) as c:
+        got = c.encode_u8(img[None], q)
+    assert _diff(o, got, want, ch) is None
+    assert np.array_equal(got, want)  # including the zeroed padding columns
+
+
+@pytest.mark.parametrize("w,h", [(512, 512), (517, 389), (250, 131), (33, 47), (129, 130), (1920, 1080)])
+@pytest.mark.parametrize("q", [0, 1, 9, 20, 31])
+@pytest.mark.parametrize("ch", [1, 3])
+def test_decode_stage(w, h, q, ch):
+    img = synth_image(1, w, h, ch)
+    trans = 1 if q == 0 else 0
+    o = oraclebind.Oracle(w, h, 5, trans=trans)
+    arenas = o.encode_image(img, q)
+    for p in range(ch):
+        o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+    want = o.decode_image(arenas, ch, q)
+    with capi.Context(w, h, ch, 5, trans=trans) as c:
+        got = c.decode_u8(arenas, 1, q)[0]
+    assert np.array_equal(got, want)
+    if q == 0 and w % 2 == 0:
+        assert np.array_equal(got, img)
+
+
+def test_batch_matches_single():
+    w, h, ch, n, q = 480, 272, 3, 5, 9
+    imgs = np.stack([synth_image(i, w, h, ch) for i in range(n)])
+    o = oraclebind.Oracle(w, h, 5)
+    with capi.Context(w, h, ch, 5, max_batch=n) as c:
+        got = c.encode_u8(imgs, q)
+        for i in range(n):
+            want = o.encode_image(imgs[i], q)
+            assert np.array_equal(got[i * c.image_arena_bytes:(i + 1) * c.image_arena_bytes], want), i
+        signed = got.copy()
+        for i in range(n * ch):
+            o.unfold(signed[i * o.arena_bytes:(i + 1) * o.arena_bytes])
+        dec = c.decode_u8(signed, n, q)
+        for i in range(n):
+            want = o.decode_image(signed[i * c.image_arena_bytes:(i + 1) * c.image_arena_bytes], ch, q)
+            assert np.array_equal(dec[i], want), i
+
+
+def test_encode_after_decode_keeps_padding_zero():
+    w, h, q = 250, 131, 9
+    img = synth_image(0, w, h, 1)
+    o = oraclebind.Oracle(w, h, 5)
+    want = o.encode_image(img, q)
+    with capi.Context(w, h, 1, 5) as c:
+        junk = np.full(c.arena_bytes, 0x5A, dtype=np.uint8)
+        c.decode_u8(junk, 1, q)
+        assert np.array_equal(c.encode_u8(img[None], q), want)
+
+
+def test_golden_full_size(golden):
+    """BASELINE.json shapes at full size against reference-generated CRCs (tests/golden/kats.json)."""
+    for k in golden["kats"]:
+        w, h, ch, q = k["w"], k["h"], k["ch"], k["q"]
+        img = synth_image(k["idx"], w, h, ch)
+        assert crc(img) == k["src_crc"]
+        o = oraclebind.Oracle(w, h, k["levels"], trans=k["trans"])
+        with capi.Context(w, h, ch, k["levels"], trans=k["trans"]) as c:
+            arenas = c.encode_u8(img[None], q)
+            assert crc(arenas) == k["enc_arena_crc"], k
+            for p in range(ch):
+                o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+            assert crc(arenas) == k["dec_arena_crc"], k
+            dec = c.decode_u8(arenas, 1, q)
+            assert crc(dec) == k["dec8_crc"], k
+
+
+def test_error_codes():
+    L = capi.lib()
+    with pytest.raises(capi.RicError) as e:
+        capi.Context(8, 8)
+    assert e.value.code == capi.E_ARG
+    with pytest.raises(capi.RicError) as e:
+        capi.Context(64, 64, trans=capi.HAAR)
+    assert e.value.code == capi.E_UNSUPPORTED
+    with capi.Context(64, 64) as c:
+        with pytest.raises(capi.RicError):
+            c.encode_u8(np.zeros((2, 1, 64, 64), np.uint8), 9)  # n > max_batch
+        with pytest.raises(capi.RicError):
+            c.encode_u8(np.zeros((1, 1, 64, 64), np.uint8), 40)
+    assert L.ric_last_error()
