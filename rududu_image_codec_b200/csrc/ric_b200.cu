@@ -58,52 +58,24 @@ struct ric_ctx {
 typedef void (*fwd_fn)(const FwdParams);
 typedef void (*inv_fn)(const InvParams);
 
-template <bool SH, int TRANS>
-static fwd_fn pick_fwd2(int src, int lldst)
+static fwd_fn pick_fwd(bool sh, int trans, int src)
 {
-	if (SH) {
-		if (src == SRC_U8_GRAY) return lldst == LL_BAND ? fwd_level_kernel<true, TRANS, SRC_U8_GRAY, LL_BAND> : fwd_level_kernel<true, TRANS, SRC_U8_GRAY, LL_S16>;
-		if (src == SRC_U8_RGB) return lldst == LL_BAND ? fwd_level_kernel<true, TRANS, SRC_U8_RGB, LL_BAND> : fwd_level_kernel<true, TRANS, SRC_U8_RGB, LL_S16>;
-		if (src == SRC_S16) return lldst == LL_BAND ? fwd_level_kernel<true, TRANS, SRC_S16, LL_BAND> : fwd_level_kernel<true, TRANS, SRC_S16, LL_S16>;
-		return nullptr;
-	}
-	if (src == SRC_S16) return lldst == LL_BAND ? fwd_level_kernel<false, TRANS, SRC_S16, LL_BAND> : fwd_level_kernel<false, TRANS, SRC_S16, LL_S32>;
-	if (src == SRC_S32) return lldst == LL_BAND ? fwd_level_kernel<false, TRANS, SRC_S32, LL_BAND> : fwd_level_kernel<false, TRANS, SRC_S32, LL_S32>;
+#define RIC_F(SHV, TR_, SRC_) if (sh == SHV && trans == (TR_ == T97 ? RIC_CDF97 : RIC_CDF53) && src == SRC_) return fwd_level_kernel<SHV, TR_, SRC_>;
+	RIC_F(true, T97, SRC_U8_GRAY) RIC_F(true, T97, SRC_U8_RGB) RIC_F(true, T97, SRC_S16)
+	RIC_F(false, T97, SRC_S16) RIC_F(false, T97, SRC_S32)
+	RIC_F(true, T53, SRC_U8_GRAY) RIC_F(true, T53, SRC_U8_RGB) RIC_F(true, T53, SRC_S16)
+	RIC_F(false, T53, SRC_S16) RIC_F(false, T53, SRC_S32)
+#undef RIC_F
 	return nullptr;
 }
 
-static fwd_fn pick_fwd(bool sh, int trans, int src, int lldst)
+static inv_fn pick_inv(bool sh, int trans, int dst)
 {
-	if (trans == RIC_CDF97) return sh ? pick_fwd2<true, T97>(src, lldst) : pick_fwd2<false, T97>(src, lldst);
-	return sh ? pick_fwd2<true, T53>(src, lldst) : pick_fwd2<false, T53>(src, lldst);
-}
-
-template <bool SH, int TRANS>
-static inv_fn pick_inv2(int llsrc, int dst)
-{
-	if (SH) {
-#define RIC_ROW(LS)                                                                        \
-	if (llsrc == LS) {                                                                     \
-		if (dst == DST_S16) return inv_level_kernel<true, TRANS, LS, DST_S16>;             \
-		if (dst == DST_U8_GRAY) return inv_level_kernel<true, TRANS, LS, DST_U8_GRAY>;     \
-		if (dst == DST_U8_RGB) return inv_level_kernel<true, TRANS, LS, DST_U8_RGB>;       \
-	}
-		RIC_ROW(LLSRC_S16)
-		RIC_ROW(LLSRC_S32)
-		RIC_ROW(LLSRC_BAND)
-#undef RIC_ROW
-		return nullptr;
-	}
-	if (dst != DST_S32) return nullptr;
-	if (llsrc == LLSRC_S32) return inv_level_kernel<false, TRANS, LLSRC_S32, DST_S32>;
-	if (llsrc == LLSRC_BAND) return inv_level_kernel<false, TRANS, LLSRC_BAND, DST_S32>;
+#define RIC_I(SHV, TR_, DST_) if (sh == SHV && trans == (TR_ == T97 ? RIC_CDF97 : RIC_CDF53) && dst == DST_) return inv_level_kernel<SHV, TR_, DST_>;
+	RIC_I(true, T97, DST_PLANE) RIC_I(true, T97, DST_U8_GRAY) RIC_I(true, T97, DST_U8_RGB) RIC_I(false, T97, DST_PLANE)
+	RIC_I(true, T53, DST_PLANE) RIC_I(true, T53, DST_U8_GRAY) RIC_I(true, T53, DST_U8_RGB) RIC_I(false, T53, DST_PLANE)
+#undef RIC_I
 	return nullptr;
-}
-
-static inv_fn pick_inv(bool sh, int trans, int llsrc, int dst)
-{
-	if (trans == RIC_CDF97) return sh ? pick_inv2<true, T97>(llsrc, dst) : pick_inv2<false, T97>(llsrc, dst);
-	return sh ? pick_inv2<true, T53>(llsrc, dst) : pick_inv2<false, T53>(llsrc, dst);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -353,7 +325,7 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 		memset(&P, 0, sizeof P);
 		const bool last = lv == g.nlev - 1;
 		const bool sh = !g.lev_int[lv];
-		int src, lldst;
+		int src;
 		if (lv == 0) {
 			P.src = d_src; src = src_kind;
 			P.src_img_stride = src_img_stride; P.src_plane_stride = src_plane_stride; P.src_pitch = src_pitch;
@@ -364,9 +336,8 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 			P.src_plane_stride = (long long)g.lev_h[lv] * P.src_pitch;
 			P.src_img_stride = P.src_plane_stride * g.channels;
 		}
-		if (last) lldst = LL_BAND;
-		else {
-			lldst = g.lev_int[lv] ? LL_S32 : LL_S16;
+		P.ll_to_band = last;
+		if (!last) {
 			P.ll = c->d_ll[lv];
 			P.ll_pitch = c->ll_pitch[lv];
 			P.ll_plane_stride = (long long)g.lev_h[lv + 1] * P.ll_pitch;
@@ -406,10 +377,10 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 				make_tsuq(Quant[p], 0.5f, g.band[3 * g.nlev].weight, g.lev_int[g.nlev - 1], &P.llQ[cls], &P.lliQ[cls], &P.llT[cls]);
 			}
 		}
-		fwd_fn fn = pick_fwd(sh, g.trans, src, lldst);
+		fwd_fn fn = pick_fwd(sh, g.trans, src);
 		if (!fn) return set_err(RIC_E_UNSUPPORTED, "forward: unsupported level type combination");
 		const long long njobs = (long long)P.nstrips * P.nsegs * nplanes * n;
-		const int wpb = 4;
+		const int wpb = fwd_warps(sh);
 		const unsigned grid = (unsigned)((njobs + wpb - 1) / wpb);
 		fn<<<grid, wpb * 32, 0, st>>>(P);
 		CK(cudaGetLastError());
@@ -433,10 +404,10 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		P.arena = d_arena;
 		P.arena_plane_stride = (long long)g.arena_bytes;
 		P.arena_img_stride = (long long)g.arena_bytes * g.channels;
-		int llsrc, dst;
-		if (coarsest) llsrc = LLSRC_BAND;
+		int dst;
+		if (coarsest) P.llsrc = LLSRC_BAND;
 		else {
-			llsrc = g.lev_int[lv + 1] ? LLSRC_S32 : LLSRC_S16;
+			P.llsrc = g.lev_int[lv + 1] ? LLSRC_S32 : LLSRC_S16;
 			P.ll = c->d_ll[lv];
 			P.ll_pitch = c->ll_pitch[lv];
 			P.ll_plane_stride = (long long)g.lev_h[lv + 1] * P.ll_pitch;
@@ -446,7 +417,7 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 			dst = dst_kind;
 			P.dst = d_dst; P.dst_img_stride = dst_img_stride; P.dst_plane_stride = dst_plane_stride; P.dst_pitch = dst_pitch;
 		} else {
-			dst = g.lev_int[lv] ? DST_S32 : DST_S16;
+			dst = DST_PLANE;
 			P.dst = c->d_ll[lv - 1];
 			P.dst_pitch = c->ll_pitch[lv - 1];
 			P.dst_plane_stride = (long long)g.lev_h[lv] * P.dst_pitch;
@@ -467,12 +438,16 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 				const int id = o < 3 ? 3 * lv + o : 3 * g.nlev;
 				P.dq[p][o] = (p < nplanes && dq_Quant[p]) ? make_tsuqi(dq_Quant[p], g.band[id].weight, g.band[id].is_int) : 1;
 			}
-		inv_fn fn = pick_inv(sh, g.trans, llsrc, dst);
+		inv_fn fn = pick_inv(sh, g.trans, dst);
 		if (!fn) return set_err(RIC_E_UNSUPPORTED, "inverse: unsupported level type combination");
 		const long long njobs = (long long)P.nstrips * P.nsegs * jplanes * n;
-		const int wpb = 4;
-		const unsigned grid = (unsigned)((njobs + wpb - 1) / wpb);
-		fn<<<grid, wpb * 32, 0, st>>>(P);
+		if (dst == DST_U8_RGB) {
+			const unsigned grid = (unsigned)((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS);
+			fn<<<grid, INV_RGB_GROUPS * 96, 0, st>>>(P);
+		} else {
+			const unsigned grid = (unsigned)((njobs + INV_WARPS - 1) / INV_WARPS);
+			fn<<<grid, INV_WARPS * 32, 0, st>>>(P);
+		}
 		CK(cudaGetLastError());
 		c->launches++;
 	}
@@ -675,7 +650,7 @@ int ric_transform_inv(ric_ctx *c, const void *arena, int16_t *plane, int stride)
 	if (rc) return rc;
 	CK(cudaMemcpyAsync(c->d_arena_in, arena, g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
 	int Q[3] = {0, 0, 0};
-	rc = launch_inverse(c, c->d_arena_in, 1, 1, 0, Q, DST_S16, c->d_plane, 0, 0, c->plane_pitch, 1, c->stream);
+	rc = launch_inverse(c, c->d_arena_in, 1, 1, 0, Q, DST_PLANE, c->d_plane, 0, 0, c->plane_pitch, 1, c->stream);
 	if (rc) return rc;
 	CK(cudaMemcpy2DAsync(plane, (size_t)stride * 2, c->d_plane, (size_t)c->plane_pitch * 2, (size_t)g.width * 2, g.height,
 	                     cudaMemcpyDeviceToHost, c->stream));

@@ -247,22 +247,21 @@ __device__ __forceinline__ int fold_s2u(int c)  // s2u_, utils.h:95-99
 	return (2 * c + m) ^ (m * 2);
 }
 
-// Batcher odd-even merge sort of 16 keys, descending, fully unrolled (63 compare-exchanges).
+// Batcher odd-even merge sort of 16 keys, descending: 63 compare-exchanges written out so that the
+// keys provably stay in registers (a rolled network would index them dynamically -> local memory).
 __device__ __forceinline__ void sort16_desc(int (&s)[16])
 {
-#pragma unroll
-	for (int p = 1; p < 16; p <<= 1)
-#pragma unroll
-		for (int k = p; k >= 1; k >>= 1)
-#pragma unroll
-			for (int j = k % p; j + k < 16; j += 2 * k)
-#pragma unroll
-				for (int i = 0; i < k; i++)
-					if (i + j + k < 16 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-						int a = s[i + j], b = s[i + j + k];
-						s[i + j] = max(a, b);
-						s[i + j + k] = min(a, b);
-					}
+#define RIC_CE(i, j) { const int a_ = s[i], b_ = s[j]; s[i] = max(a_, b_); s[j] = min(a_, b_); }
+	RIC_CE(0, 1) RIC_CE(2, 3) RIC_CE(4, 5) RIC_CE(6, 7) RIC_CE(8, 9) RIC_CE(10, 11) RIC_CE(12, 13)
+	RIC_CE(14, 15) RIC_CE(0, 2) RIC_CE(1, 3) RIC_CE(4, 6) RIC_CE(5, 7) RIC_CE(8, 10) RIC_CE(9, 11)
+	RIC_CE(12, 14) RIC_CE(13, 15) RIC_CE(1, 2) RIC_CE(5, 6) RIC_CE(9, 10) RIC_CE(13, 14) RIC_CE(0, 4)
+	RIC_CE(1, 5) RIC_CE(2, 6) RIC_CE(3, 7) RIC_CE(8, 12) RIC_CE(9, 13) RIC_CE(10, 14) RIC_CE(11, 15)
+	RIC_CE(2, 4) RIC_CE(3, 5) RIC_CE(10, 12) RIC_CE(11, 13) RIC_CE(1, 2) RIC_CE(3, 4) RIC_CE(5, 6)
+	RIC_CE(9, 10) RIC_CE(11, 12) RIC_CE(13, 14) RIC_CE(0, 8) RIC_CE(1, 9) RIC_CE(2, 10) RIC_CE(3, 11)
+	RIC_CE(4, 12) RIC_CE(5, 13) RIC_CE(6, 14) RIC_CE(7, 15) RIC_CE(4, 8) RIC_CE(5, 9) RIC_CE(6, 10)
+	RIC_CE(7, 11) RIC_CE(2, 4) RIC_CE(3, 5) RIC_CE(6, 8) RIC_CE(7, 9) RIC_CE(10, 12) RIC_CE(11, 13)
+	RIC_CE(1, 2) RIC_CE(3, 4) RIC_CE(5, 6) RIC_CE(7, 8) RIC_CE(9, 10) RIC_CE(11, 12) RIC_CE(13, 14)
+#undef RIC_CE
 }
 
 // Quantise one 4x4 block held in registers (c[4*row+col], proper C values), in place, returning

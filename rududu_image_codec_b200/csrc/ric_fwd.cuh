@@ -16,12 +16,16 @@
 // level samples), quantised in registers and written once, in the band layout the entropy coder
 // reads.  No shared-memory staging of samples, no block-level synchronisation in the main loop.
 #pragma once
+#include <type_traits>
+
 #include "ric_dev.cuh"
 
 namespace ric {
 
 enum { SRC_U8_GRAY = 0, SRC_U8_RGB = 1, SRC_S16 = 2, SRC_S32 = 3 };
-enum { LL_S16 = 0, LL_S32 = 1, LL_BAND = 2 };
+
+__host__ __device__ constexpr int fwd_warps(bool sh) { return sh ? 4 : 2; }  // warps per CTA (independent jobs)
+constexpr int RING_ROWS = 8;   // band rows staged per warp before a 4x4 block row is flushed
 
 struct BandRef {
 	long long off;  // byte offset inside one plane arena
@@ -35,16 +39,17 @@ struct FwdParams {
 	long long src_img_stride;  // elements between images
 	long long src_plane_stride;  // elements between planes (u8: between channels)
 	int src_pitch;             // elements between rows
-	void *ll;                  // LL scratch of this level's output (next level's input)
+	void *ll;                  // LL scratch of this level's output (next level's input); s16 (short level) / s32
 	long long ll_img_stride, ll_plane_stride;
 	int ll_pitch;
+	int ll_to_band;            // last level: LL goes to the L band (with TSUQ when quant)
 	char *arena;               // band arenas
 	long long arena_img_stride, arena_plane_stride;  // bytes
 	unsigned char *flags;      // block non-zero flags (pRD != 0), all levels
 	long long flags_img_stride, flags_plane_stride;
 	BandRef band[3];           // D, H, V of this level
 	BandRef child[3];          // same orientation one level finer (has_child)
-	BandRef lband;             // LL band (LL_BAND only)
+	BandRef lband;             // LL band (ll_to_band)
 	int has_child;
 	int w, h;                  // level input size
 	int nstrips, nsegs, seg_rows, nplanes, nimages;
@@ -61,10 +66,11 @@ struct RawRow {
 	unsigned r[N];
 };
 
-// issue the global loads of one row (8 columns starting at cb) -- conversion happens later
+// issue the global loads of one row (8 columns starting at cb) -- conversion happens later.
+// RGB: plane 0 (Co) does not need G.
 template <int SRC>
 __device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const void *base, long long row_off, int cb, bool ok,
-                                         long long plane_stride)
+                                         long long plane_stride, int plane)
 {
 #pragma unroll
 	for (int i = 0; i < RawRow<SRC>::N; i++) raw.r[i] = 0;
@@ -74,11 +80,14 @@ __device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const void *base, lon
 		raw.r[0] = a.x; raw.r[1] = a.y;
 	} else if (SRC == SRC_U8_RGB) {
 		const unsigned char *p = (const unsigned char *)base + row_off + cb;
-#pragma unroll
-		for (int ch = 0; ch < 3; ch++) {
-			uint2 a = __ldg((const uint2 *)(p + ch * plane_stride));
-			raw.r[2 * ch] = a.x; raw.r[2 * ch + 1] = a.y;
+		uint2 a = __ldg((const uint2 *)p);
+		raw.r[0] = a.x; raw.r[1] = a.y;
+		if (plane != 0) {
+			uint2 g = __ldg((const uint2 *)(p + plane_stride));
+			raw.r[2] = g.x; raw.r[3] = g.y;
 		}
+		uint2 b = __ldg((const uint2 *)(p + 2 * plane_stride));
+		raw.r[4] = b.x; raw.r[5] = b.y;
 	} else if (SRC == SRC_S16) {
 		uint4 a = __ldg((const uint4 *)((const short *)base + row_off + cb));
 		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = a.z; raw.r[3] = a.w;
@@ -92,30 +101,40 @@ __device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const void *base, lon
 
 __device__ __forceinline__ int byte_of(unsigned lo, unsigned hi, int k)
 {
-	return (int)(((k < 4 ? lo : hi) >> (8 * (k & 3))) & 0xFF);
+	return (int)__byte_perm(k < 4 ? lo : hi, 0, 0x4440 | (k & 3));
 }
 
-// raw registers -> 8 level-input samples (colour transform / level shift fused here)
+// raw registers -> 8 level-input samples (colour transform / level shift fused here).
+// `plane` is warp-uniform: each branch computes only what its plane needs.
 template <int SRC>
 __device__ __forceinline__ void convert_raw(const RawRow<SRC> &raw, int (&v)[8], int plane, int shift)
 {
 	if (SRC == SRC_U8_GRAY) {
+		const int sh = shift ? 4 : 0;
 #pragma unroll
-		for (int k = 0; k < 8; k++) {
-			int p = byte_of(raw.r[0], raw.r[1], k) - 128;   // ric.cpp:144 / :147
-			v[k] = shift ? p << 4 : p;
-		}
+		for (int k = 0; k < 8; k++) v[k] = (byte_of(raw.r[0], raw.r[1], k) - 128) << sh;  // ric.cpp:144 / :147
 	} else if (SRC == SRC_U8_RGB) {
+		// RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y)
+		if (plane == 0) {
+			const int sh = shift ? 3 : 0;
 #pragma unroll
-		for (int k = 0; k < 8; k++) {  // RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y)
-			int R = byte_of(raw.r[0], raw.r[1], k), G = byte_of(raw.r[2], raw.r[3], k), B = byte_of(raw.r[4], raw.r[5], k);
-			int co = R - B;
-			int t = B + (co >> 1);
-			int cg = G - t;
-			int y = t + ((cg >> 1) - 128);
-			int o = plane == 0 ? co : plane == 1 ? cg : y;
-			int sh = plane == 2 ? 4 : 3;
-			v[k] = shift ? o << sh : o;
+			for (int k = 0; k < 8; k++) v[k] = (byte_of(raw.r[0], raw.r[1], k) - byte_of(raw.r[4], raw.r[5], k)) << sh;
+		} else if (plane == 1) {
+			const int sh = shift ? 3 : 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				int R = byte_of(raw.r[0], raw.r[1], k), G = byte_of(raw.r[2], raw.r[3], k), B = byte_of(raw.r[4], raw.r[5], k);
+				int t = B + ((R - B) >> 1);
+				v[k] = (G - t) << sh;
+			}
+		} else {
+			const int sh = shift ? 4 : 0;
+#pragma unroll
+			for (int k = 0; k < 8; k++) {
+				int R = byte_of(raw.r[0], raw.r[1], k), G = byte_of(raw.r[2], raw.r[3], k), B = byte_of(raw.r[4], raw.r[5], k);
+				int t = B + ((R - B) >> 1);
+				v[k] = (t + (((G - t) >> 1) - 128)) << sh;
+			}
 		}
 	} else if (SRC == SRC_S16) {
 #pragma unroll
@@ -142,52 +161,94 @@ __device__ __forceinline__ void store4(char *rowp, int col, int c0, int c1, int 
 	}
 }
 
-// Quantise (optionally) and write one lane's 4x4 block of band `b`; bx/by: block coordinates.
+// per-warp staging ring of finished band rows: [band][row & 7][lane] -> 4 samples (lane-private)
 template <bool SH>
-__device__ __forceinline__ void flush_block(const FwdParams &P, const BandRef &b, const BandRef &ch, char *arena,
-                                            unsigned char *flags, const QuantBand *qb, int (&c)[16], int bx, int by,
-                                            bool lane_ok)
+struct Ring {
+	typedef typename std::conditional<SH, uint2, int4>::type vec;
+	vec v[3][RING_ROWS][32];
+};
+
+template <bool SH>
+__device__ __forceinline__ void ring_put(Ring<SH> &rg, int o, int row, int lane, int c0, int c1, int c2, int c3)
 {
-	const int x0 = bx * 4, y0 = by * 4;
-	if (!lane_ok || x0 >= b.dimx || y0 >= b.dimy) return;  // (warp-divergent exit is fine: no syncs below but __any)
-	const int bw = min(4, b.dimx - x0), bh = min(4, b.dimy - y0);
-	if (P.quant) {
-		int cnt = quant_block<SH>(c, qb, bw, bh);
-		int nz = cnt;
-		if (P.has_child && bw == 4 && bh == 4) {  // buildTree :267-270: add the four child blocks
-			const unsigned char *cf = flags + ch.fl_off + (2 * by) * ch.fl_bw + 2 * bx;
-			nz += cf[0] + cf[1] + cf[ch.fl_bw] + cf[ch.fl_bw + 1];
-		}
-		flags[b.fl_off + by * b.fl_bw + bx] = nz != 0;
-		if (nz == 0) c[0] = -0x8000;  // INSIGNIF_BLOCK, bandcodec.cpp:113,272
-	}
-	char *base = arena + b.off;
-	const int es = SH ? 2 : 4;
-	if (bw == 4) {
-#pragma unroll
-		for (int r = 0; r < 4; r++)
-			if (r < bh) store4<SH>(base + (long long)(y0 + r) * b.stride * es, x0, c[4 * r], c[4 * r + 1], c[4 * r + 2], c[4 * r + 3]);
+	if (SH) {
+		uint2 t;
+		t.x = (unsigned)(c0 & 0xFFFF) | ((unsigned)c1 << 16);
+		t.y = (unsigned)(c2 & 0xFFFF) | ((unsigned)c3 << 16);
+		*(uint2 *)&rg.v[o][row & (RING_ROWS - 1)][lane] = t;
 	} else {
-#pragma unroll
-		for (int r = 0; r < 4; r++)
-#pragma unroll
-			for (int k = 0; k < 4; k++)
-				if (r < bh && k < bw) {
-					char *p = base + ((long long)(y0 + r) * b.stride + x0 + k) * es;
-					if (SH) *(short *)p = (short)c[4 * r + k]; else *(int *)p = c[4 * r + k];
-				}
+		*(int4 *)&rg.v[o][row & (RING_ROWS - 1)][lane] = make_int4(c0, c1, c2, c3);
 	}
 }
 
-template <bool SH, int TRANS, int SRC, int LLDST>
-__global__ void __launch_bounds__(128) fwd_level_kernel(const __grid_constant__ FwdParams P)
+template <bool SH>
+__device__ __forceinline__ void ring_get(const Ring<SH> &rg, int o, int row, int lane, int &c0, int &c1, int &c2, int &c3)
+{
+	if (SH) {
+		uint2 t = *(const uint2 *)&rg.v[o][row & (RING_ROWS - 1)][lane];
+		c0 = (int)(short)(t.x & 0xFFFF); c1 = (int)t.x >> 16;
+		c2 = (int)(short)(t.y & 0xFFFF); c3 = (int)t.y >> 16;
+	} else {
+		int4 t = *(const int4 *)&rg.v[o][row & (RING_ROWS - 1)][lane];
+		c0 = t.x; c1 = t.y; c2 = t.z; c3 = t.w;
+	}
+}
+
+// Quantise (optionally) and write block row `by` of the three bands from the staging ring.
+// One lane = one 4x4 block per band (bx = this lane's block column).
+template <bool SH>
+__device__ __forceinline__ void flush_blocks(const FwdParams &P, const Ring<SH> &rg, char *arena, unsigned char *flags,
+                                          const QuantBand *qb3, int bx, int by, int lane)
+{
+#pragma unroll 1
+	for (int o = 0; o < 3; o++) {
+		const BandRef &b = P.band[o];
+		const int x0 = bx * 4, y0 = by * 4;
+		if (x0 >= b.dimx || y0 >= b.dimy) continue;
+		const int bw = min(4, b.dimx - x0), bh = min(4, b.dimy - y0);
+		int c[16];
+#pragma unroll
+		for (int r = 0; r < 4; r++) ring_get<SH>(rg, o, y0 + r, lane, c[4 * r], c[4 * r + 1], c[4 * r + 2], c[4 * r + 3]);
+		if (P.quant) {
+			int nz = quant_block<SH>(c, qb3 + o, bw, bh);
+			if (P.has_child && bw == 4 && bh == 4) {  // buildTree :267-270: add the four child blocks
+				const BandRef &ch = P.child[o];
+				const unsigned char *cf = flags + ch.fl_off + (2 * by) * ch.fl_bw + 2 * bx;
+				nz += cf[0] + cf[1] + cf[ch.fl_bw] + cf[ch.fl_bw + 1];  // (odd fl_bw: the second row is not 2-byte aligned)
+			}
+			flags[b.fl_off + by * b.fl_bw + bx] = nz != 0;
+			if (nz == 0) c[0] = -0x8000;  // INSIGNIF_BLOCK, bandcodec.cpp:113,272
+		}
+		char *base = arena + b.off;
+		const int es = SH ? 2 : 4;
+		if (bw == 4) {
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+				if (r < bh) store4<SH>(base + (long long)(y0 + r) * b.stride * es, x0, c[4 * r], c[4 * r + 1], c[4 * r + 2], c[4 * r + 3]);
+		} else {
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					if (r < bh && k < bw) {
+						char *p = base + ((long long)(y0 + r) * b.stride + x0 + k) * es;
+						if (SH) *(short *)p = (short)c[4 * r + k]; else *(int *)p = c[4 * r + k];
+					}
+		}
+	}
+}
+
+template <bool SH, int TRANS, int SRC>
+__global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const __grid_constant__ FwdParams P)
 {
 	__shared__ QuantBand s_qb[2][3];
+	constexpr int FWD_WARPS = fwd_warps(SH);
+	__shared__ Ring<SH> s_ring[FWD_WARPS];
 	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
 	__syncthreads();
 
-	const int lane = threadIdx.x & 31;
-	long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	long long job = (long long)blockIdx.x * FWD_WARPS + wib;
 	const long long njobs = (long long)P.nstrips * P.nplanes * P.nsegs * P.nimages;
 	if (job >= njobs) return;
 	// plane fastest: the planes of one RGB strip share their u8 loads through L1
@@ -195,6 +256,7 @@ __global__ void __launch_bounds__(128) fwd_level_kernel(const __grid_constant__ 
 	const int sx = (int)(job % P.nstrips); job /= P.nstrips;
 	const int sy = (int)(job % P.nsegs);
 	const int img = (int)(job / P.nsegs);
+	Ring<SH> &rg = s_ring[wib];
 
 	const int w = P.w, h = P.h;
 	const int x0 = sx * STRIP_W;
@@ -216,113 +278,93 @@ __global__ void __launch_bounds__(128) fwd_level_kernel(const __grid_constant__ 
 	char *arena = P.arena + img * P.arena_img_stride + plane * P.arena_plane_stride;
 	unsigned char *flags = P.flags + img * P.flags_img_stride + plane * P.flags_plane_stride;
 	const int cls = P.plane_class[plane];
-	const QuantBand *qbD = &s_qb[cls][0], *qbH = &s_qb[cls][1], *qbV = &s_qb[cls][2];
 	const int bx = cb >> 3;  // block column of this lane in every band of this level
+	const int lx = cb >> 1;  // first LL column of this lane
+	char *ll_base;           // LL destination (row 0)
+	int ll_rowbytes;
+	if (P.ll_to_band) {
+		ll_base = arena + P.lband.off;
+		ll_rowbytes = P.lband.stride * (SH ? 2 : 4);
+	} else {
+		ll_base = (char *)P.ll + (img * P.ll_img_stride + plane * P.ll_plane_stride) * (SH ? 2 : 4);
+		ll_rowbytes = P.ll_pitch * (SH ? 2 : 4);
+	}
+	const int ll_dimx = w >> 1;
 
 	// vertical state: so1 raw odd row 2t-1, se1 S1'd even row 2t-2, so2 S2'd odd row 2t-3, se3 S3'd even row 2t-4
 	int so1[8], se1[8], so2[8], se3[8];
 #pragma unroll
 	for (int k = 0; k < 8; k++) so1[k] = se1[k] = so2[k] = se3[k] = 0;
-	int bD[16], bH[16], bV[16];
-#pragma unroll
-	for (int k = 0; k < 16; k++) bD[k] = bH[k] = bV[k] = 0;
 
-	const int t_begin = (y0 >> 1) - 2, t_end = (y1r >> 1) + 2;  // exclusive; (t_end - t_begin) % 4 == 0
+	const int t_begin = (y0 >> 1) - 2, t_last = (y1r >> 1) + 1;
 	RawRow<SRC> rawE, rawO;
 	{
 		int re = 2 * t_begin, ro = re + 1;
-		load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride);
-		load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride);
+		load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
+		load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 	}
 
-	for (int t0 = t_begin; t0 < t_end; t0 += 4) {
-		// rows touched by this group: 2*t0-4 .. 2*t0+7; edge formulas needed if that range meets row 0 or h-1
-		const bool edge_y = (2 * t0 - 4 <= 0) || (2 * t0 + 7 >= h - 1);
-#pragma unroll
-		for (int u = 0; u < 4; u++) {
-			const int t = t0 + u;
-			int ne[8], no[8];
-			convert_raw<SRC>(rawE, ne, plane, P.shift);
-			convert_raw<SRC>(rawO, no, plane, P.shift);
-			{  // prefetch the next row pair
-				int re = 2 * t + 2, ro = re + 1;
-				load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride);
-				load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride);
-			}
-			if (edge_x) { row_fwd<SH, TRANS, true>(ne, cb, w); row_fwd<SH, TRANS, true>(no, cb, w); }
-			else { row_fwd<SH, TRANS, false>(ne, cb, w); row_fwd<SH, TRANS, false>(no, cb, w); }
-
-			const int r1 = 2 * t, r2 = 2 * t - 1, r3 = 2 * t - 2, r4 = 2 * t - 3;
-			if (edge_y) {
-				if (r1 >= 0 && r1 < h) vS1<SH, TRANS, true>(ne, so1, no, r1 == 0, r1 == h - 1);
-				if (r2 >= 0 && r2 < h) vS2<SH, TRANS, true>(so1, se1, ne, false, r2 == h - 1);
-				if (r3 >= 0 && r3 < h) vS3<SH, TRANS, true>(se1, so2, so1, r3 == 0, r3 == h - 1);
-				if (r4 >= 0 && r4 < h) vS4<SH, TRANS, true>(so2, se3, se1, false, r4 == h - 1);
-			} else {
-				vS1<SH, TRANS, false>(ne, so1, no, false, false);
-				vS2<SH, TRANS, false>(so1, se1, ne, false, false);
-				vS3<SH, TRANS, false>(se1, so2, so1, false, false);
-				vS4<SH, TRANS, false>(so2, se3, se1, false, false);
-			}
-			// finished: even row r3 (band row jd = t-1: D even cols, H odd cols), odd row r4 (band row jv = t-2: V, LL)
-			const int jd = t - 1, jv = t - 2;
-			constexpr int UD = 0, UV = 0;
-			(void)UD; (void)UV;
-			const int sd = (u + 1) & 3, sv = u & 3;  // slot of jd / jv inside its 4-row block (y0/2 is a multiple of 4)
-#pragma unroll
-			for (int k = 0; k < 4; k++) {
-				bD[4 * sd + k] = se1[2 * k];
-				bH[4 * sd + k] = se1[2 * k + 1];
-				bV[4 * sv + k] = so2[2 * k];
-			}
-			// LL row jv
-			if (jv >= (y0 >> 1) && jv < (y1 >> 1) && lane_out) {
-				int llv[4];
-#pragma unroll
-				for (int k = 0; k < 4; k++) llv[k] = so2[2 * k + 1];
-				const int lx = cb >> 1;
-				if (LLDST == LL_BAND) {
-					const BandRef &L = P.lband;
-					if (P.quant) {
-#pragma unroll
-						for (int k = 0; k < 4; k++) llv[k] = tsuq1<SH>(llv[k], P.llT[cls], P.lliQ[cls]);
-					}
-					char *rowp = arena + L.off + (long long)jv * L.stride * (SH ? 2 : 4);
-					if (lx + 4 <= L.dimx) store4<SH>(rowp, lx, llv[0], llv[1], llv[2], llv[3]);
-					else {
-#pragma unroll
-						for (int k = 0; k < 4; k++)
-							if (lx + k < L.dimx) {
-								if (SH) ((short *)rowp)[lx + k] = (short)llv[k]; else ((int *)rowp)[lx + k] = llv[k];
-							}
-					}
-				} else if (lx < (w >> 1)) {
-					// scratch rows are padded to a multiple of 8 samples: a full 4-sample store is always in bounds
-					if (LLDST == LL_S16) {
-						short *rowp = (short *)P.ll + img * P.ll_img_stride + plane * P.ll_plane_stride + (long long)jv * P.ll_pitch;
-						store4<true>((char *)rowp, lx, llv[0], llv[1], llv[2], llv[3]);
-					} else {
-						int *rowp = (int *)P.ll + img * P.ll_img_stride + plane * P.ll_plane_stride + (long long)jv * P.ll_pitch;
-						store4<false>((char *)rowp, lx, llv[0], llv[1], llv[2], llv[3]);
-					}
-				}
-			}
-			if (u == 2) {  // D/H block row (jd>>2) complete
-				const int by = jd >> 2;
-				if (by >= (y0 >> 3) && by < (y1r >> 3)) {
-					flush_block<SH>(P, P.band[0], P.child[0], arena, flags, qbD, bD, bx, by, lane_out);
-					flush_block<SH>(P, P.band[1], P.child[1], arena, flags, qbH, bH, bx, by, lane_out);
-				}
-			}
-			if (u == 3) {  // V block row (jv>>2) complete
-				const int by = jv >> 2;
-				if (by >= (y0 >> 3) && by < (y1r >> 3))
-					flush_block<SH>(P, P.band[2], P.child[2], arena, flags, qbV, bV, bx, by, lane_out);
-			}
-			// rotate the vertical state
-#pragma unroll
-			for (int k = 0; k < 8; k++) { se3[k] = se1[k]; so2[k] = so1[k]; se1[k] = ne[k]; so1[k] = no[k]; }
+#pragma unroll 1
+	for (int t = t_begin; t <= t_last; t++) {
+		int ne[8], no[8];
+		convert_raw<SRC>(rawE, ne, plane, P.shift);
+		convert_raw<SRC>(rawO, no, plane, P.shift);
+		{  // prefetch the next row pair
+			int re = 2 * t + 2, ro = re + 1;
+			load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
+			load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 		}
+		if (edge_x) { row_fwd<SH, TRANS, true>(ne, cb, w); row_fwd<SH, TRANS, true>(no, cb, w); }
+		else { row_fwd<SH, TRANS, false>(ne, cb, w); row_fwd<SH, TRANS, false>(no, cb, w); }
+
+		const int r1 = 2 * t, r2 = 2 * t - 1, r3 = 2 * t - 2, r4 = 2 * t - 3;
+		// rows r4-1 .. r1+1 are touched; edge formulas if that range meets row 0 or row h-1
+		const bool edge_y = (r4 - 1 <= 0) || (r1 + 1 >= h - 1);
+		if (edge_y) {
+			if (r1 >= 0 && r1 < h) vS1<SH, TRANS, true>(ne, so1, no, r1 == 0, r1 == h - 1);
+			if (r2 >= 0 && r2 < h) vS2<SH, TRANS, true>(so1, se1, ne, false, r2 == h - 1);
+			if (r3 >= 0 && r3 < h) vS3<SH, TRANS, true>(se1, so2, so1, r3 == 0, r3 == h - 1);
+			if (r4 >= 0 && r4 < h) vS4<SH, TRANS, true>(so2, se3, se1, false, r4 == h - 1);
+		} else {
+			vS1<SH, TRANS, false>(ne, so1, no, false, false);
+			vS2<SH, TRANS, false>(so1, se1, ne, false, false);
+			vS3<SH, TRANS, false>(se1, so2, so1, false, false);
+			vS4<SH, TRANS, false>(so2, se3, se1, false, false);
+		}
+		// finished: even row r3 (band row jd = t-1: D even cols, H odd cols), odd row r4 (band row jv = t-2: V, LL)
+		const int jd = t - 1, jv = t - 2;
+		ring_put<SH>(rg, 0, jd, lane, se1[0], se1[2], se1[4], se1[6]);
+		ring_put<SH>(rg, 1, jd, lane, se1[1], se1[3], se1[5], se1[7]);
+		ring_put<SH>(rg, 2, jv, lane, so2[0], so2[2], so2[4], so2[6]);
+		if (jv >= (y0 >> 1) && jv < (y1 >> 1) && lane_out && lx < ll_dimx) {  // LL row jv
+			int l0 = so2[1], l1 = so2[3], l2 = so2[5], l3 = so2[7];
+			char *rowp = ll_base + (long long)jv * ll_rowbytes;
+			if (P.ll_to_band) {
+				if (P.quant) {  // CBand::TSUQ(Quant, 0.5), wavelet2d.cpp:121,124
+					const int T = P.llT[cls], iQ = P.lliQ[cls];
+					l0 = tsuq1<SH>(l0, T, iQ); l1 = tsuq1<SH>(l1, T, iQ); l2 = tsuq1<SH>(l2, T, iQ); l3 = tsuq1<SH>(l3, T, iQ);
+				}
+				if (lx + 4 <= ll_dimx) store4<SH>(rowp, lx, l0, l1, l2, l3);
+				else {
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						if (lx + k < ll_dimx) {
+							const int lv = k == 0 ? l0 : k == 1 ? l1 : k == 2 ? l2 : l3;
+							if (SH) ((short *)rowp)[lx + k] = (short)lv; else ((int *)rowp)[lx + k] = lv;
+						}
+				}
+			} else {
+				// scratch rows are padded to a multiple of 8 samples: a full 4-sample store is always in bounds
+				store4<SH>(rowp, lx, l0, l1, l2, l3);
+			}
+		}
+		if ((jv & 3) == 3) {  // block row jv>>2 of D, H and V is complete (D/H rows sit one slot ahead in the ring)
+			const int by = jv >> 2;
+			if (by >= (y0 >> 3) && lane_out) flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane);
+		}
+		// rotate the vertical state
+#pragma unroll
+		for (int k = 0; k < 8; k++) { se3[k] = se1[k]; so2[k] = so1[k]; se1[k] = ne[k]; so1[k] = no[k]; }
 	}
 }
 

@@ -9,8 +9,9 @@
 //
 // Same warp-per-strip streaming structure as the forward kernel (ric_fwd.cuh): vertical inverse
 // lifting as a 4-row register pipeline, then the horizontal inverse on each finished row with
-// shuffles for the neighbours.  For RGB output one warp carries all three planes of its strip so
-// that the colour transform happens in registers (NPL = 3).
+// shuffles for the neighbours.  For RGB output the Co, Cg and Y warps of one strip segment form a
+// group that swaps finished rows through shared memory every third iteration, so that each warp
+// converts one iteration's pixels to RGB (no s16 plane ever goes to HBM).
 #pragma once
 #include "ric_dev.cuh"
 #include "ric_fwd.cuh"  // BandRef
@@ -18,7 +19,10 @@
 namespace ric {
 
 enum { LLSRC_S16 = 0, LLSRC_S32 = 1, LLSRC_BAND = 2 };
-enum { DST_S16 = 0, DST_S32 = 1, DST_U8_GRAY = 2, DST_U8_RGB = 3 };
+enum { DST_PLANE = 0, DST_U8_GRAY = 1, DST_U8_RGB = 2 };  // DST_PLANE: s16 (short level) / s32 scratch or plane
+
+constexpr int INV_WARPS = 4;       // warps per CTA, independent jobs (DST_PLANE / DST_U8_GRAY)
+constexpr int INV_RGB_GROUPS = 2;  // DST_U8_RGB: groups of 3 warps (Co, Cg, Y of one strip segment) per CTA
 
 struct InvParams {
 	const char *arena;
@@ -26,7 +30,8 @@ struct InvParams {
 	const void *ll;            // LL scratch written by the coarser level (LLSRC_S16/S32)
 	long long ll_img_stride, ll_plane_stride;
 	int ll_pitch;
-	void *dst;                 // scratch plane (DST_S16/S32) or u8 image
+	int llsrc;                 // LLSRC_*
+	void *dst;                 // scratch plane / s16 plane (DST_PLANE) or u8 image
 	long long dst_img_stride, dst_plane_stride;
 	int dst_pitch;
 	BandRef band[3];           // D, H, V
@@ -39,33 +44,111 @@ struct InvParams {
 	int dq[3][4];              // TSUQi multiplier per plane for D,H,V,L (1 = no dequantisation)
 };
 
+__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+
+// raw (not yet unpacked) inputs of one iteration: D/H row t, V/LL row t-1, 4 samples each
 template <bool SH>
-__device__ __forceinline__ void load4(const char *rowp, int col, bool ok, int (&o)[4])
+struct RawIn {
+	typedef typename std::conditional<SH, uint2, int4>::type vec;
+	vec d, h, v;
+	int4 l;
+};
+
+template <bool SH>
+__device__ __forceinline__ typename RawIn<SH>::vec ldvec(const char *rowp, int col, bool ok)
 {
-	if (!ok) { o[0] = o[1] = o[2] = o[3] = 0; return; }
+	typename RawIn<SH>::vec z;
+	if (SH) { uint2 t = make_uint2(0, 0); if (ok) t = __ldg((const uint2 *)(rowp + 2 * (long long)col)); *(uint2 *)&z = t; }
+	else { int4 t = make_int4(0, 0, 0, 0); if (ok) t = __ldg((const int4 *)(rowp + 4 * (long long)col)); *(int4 *)&z = t; }
+	return z;
+}
+
+template <bool SH>
+__device__ __forceinline__ void unpack4(const typename RawIn<SH>::vec &r, int (&o)[4])
+{
 	if (SH) {
-		uint2 a = __ldg((const uint2 *)(rowp + 2 * (long long)col));
+		const uint2 a = *(const uint2 *)&r;
 		o[0] = (int)(short)(a.x & 0xFFFF); o[1] = (int)a.x >> 16;
 		o[2] = (int)(short)(a.y & 0xFFFF); o[3] = (int)a.y >> 16;
 	} else {
-		int4 a = __ldg((const int4 *)(rowp + 4 * (long long)col));
+		const int4 a = *(const int4 *)&r;
 		o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
 	}
 }
 
-__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
-
-// SH: this level works on short; LLSRC: where the LL samples come from; DST: what is written.
-template <bool SH, int TRANS, int LLSRC, int DST>
-__global__ void __launch_bounds__(128) inv_level_kernel(const __grid_constant__ InvParams P)
+template <bool SH>
+__device__ __forceinline__ void load_in(RawIn<SH> &in, const InvParams &P, const char *arena, const char *llp, int t,
+                                        int bc, bool col_ok)
 {
-	constexpr int NPL = DST == DST_U8_RGB ? 3 : 1;
-	const int lane = threadIdx.x & 31;
-	long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-	const int jplanes = NPL == 3 ? 1 : P.nplanes;
+	constexpr int ES = SH ? 2 : 4;
+	const int h = P.h;
+	const bool e_ok = col_ok && 2 * t < h;
+	const bool o_ok = col_ok && t >= 1 && 2 * t - 1 < h;
+	const BandRef &D = P.band[0], &H = P.band[1], &V = P.band[2];
+	in.d = ldvec<SH>(arena + D.off + (long long)t * D.stride * ES, bc, e_ok && bc < D.dimx);
+	const long long hoff = t == 1 ? (long long)P.h_row1_off : (long long)t * H.stride;
+	in.h = ldvec<SH>(arena + H.off + hoff * ES, bc, e_ok && bc < H.dimx);
+	in.v = ldvec<SH>(arena + V.off + (long long)(t - 1) * V.stride * ES, bc, o_ok && bc < V.dimx);
+	in.l = make_int4(0, 0, 0, 0);
+	const bool l_ok = o_ok && bc < (P.w >> 1);
+	if (P.llsrc == LLSRC_BAND) {
+		typename RawIn<SH>::vec r = ldvec<SH>(arena + P.lband.off + (long long)(t - 1) * P.lband.stride * ES, bc, l_ok);
+		if (SH) { const uint2 a = *(const uint2 *)&r; in.l.x = (int)a.x; in.l.y = (int)a.y; }
+		else in.l = *(const int4 *)&r;
+	} else if (P.llsrc == LLSRC_S16) {
+		uint2 a = make_uint2(0, 0);
+		if (l_ok) a = __ldg((const uint2 *)(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 2));
+		in.l.x = (int)a.x; in.l.y = (int)a.y;
+	} else {
+		if (l_ok) in.l = __ldg((const int4 *)(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 4));
+	}
+}
+
+// unpack + dequantise (TSUQi: pBand[n] *= Quant, truncating store) into interleaved even/odd rows
+template <bool SH>
+__device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &P, int plane, int (&xe)[8], int (&xo)[8])
+{
+	int d[4], hh[4], v[4], l[4];
+	unpack4<SH>(in.d, d);
+	unpack4<SH>(in.h, hh);
+	unpack4<SH>(in.v, v);
+	if (P.llsrc == LLSRC_S32 || (!SH && P.llsrc == LLSRC_BAND)) {
+		l[0] = in.l.x; l[1] = in.l.y; l[2] = in.l.z; l[3] = in.l.w;
+	} else {
+		l[0] = (int)(short)(in.l.x & 0xFFFF); l[1] = in.l.x >> 16;
+		l[2] = (int)(short)(in.l.y & 0xFFFF); l[3] = in.l.y >> 16;
+	}
+	const int qd = P.dq[plane][0], qh = P.dq[plane][1], qv = P.dq[plane][2];
+	const int ql = P.llsrc == LLSRC_BAND ? P.dq[plane][3] : 1;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		xe[2 * k] = TR<SH>(d[k] * qd);
+		xe[2 * k + 1] = TR<SH>(hh[k] * qh);
+		xo[2 * k] = TR<SH>(v[k] * qv);
+		xo[2 * k + 1] = TR<SH>(l[k] * ql);  // also the (C) narrowing of an int LL, wavelet2d.cpp:971-980
+	}
+}
+
+__device__ __forceinline__ unsigned pack2(int a, int b) { return (unsigned)(a & 0xFFFF) | ((unsigned)b << 16); }
+__device__ __forceinline__ unsigned pack4b(unsigned a, unsigned b, unsigned c, unsigned d) { return a | b << 8 | c << 16 | d << 24; }
+
+// SH: this level works on short; DST: what is written.
+template <bool SH, int TRANS, int DST>
+__global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_WARPS * 32, DST == DST_U8_RGB ? 3 : 4)
+    inv_level_kernel(const __grid_constant__ InvParams P)
+{
+	constexpr bool RGB = DST == DST_U8_RGB;
+	// RGB staging: [group][slot][plane][row parity][lane] -> 8 s16 samples
+	__shared__ uint4 s_stage[RGB ? INV_RGB_GROUPS : 1][RGB ? 3 : 1][RGB ? 3 : 1][RGB ? 2 : 1][RGB ? 32 : 1];
+
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int grp = RGB ? wib / 3 : 0;
+	long long job = RGB ? (long long)blockIdx.x * INV_RGB_GROUPS + grp : (long long)blockIdx.x * INV_WARPS + wib;
+	const int jplanes = RGB ? 1 : P.nplanes;
 	const long long njobs = (long long)P.nstrips * jplanes * P.nsegs * P.nimages;
-	if (job >= njobs) return;
-	const int plane0 = (int)(job % jplanes); job /= jplanes;
+	if (job >= njobs) return;  // RGB: the three warps of a group leave together
+	const int plane = RGB ? wib % 3 : (int)(job % jplanes);
+	job /= jplanes;
 	const int sx = (int)(job % P.nstrips); job /= P.nstrips;
 	const int sy = (int)(job % P.nsegs);
 	const int img = (int)(job / P.nsegs);
@@ -79,102 +162,68 @@ __global__ void __launch_bounds__(128) inv_level_kernel(const __grid_constant__ 
 	const int y0 = sy * P.seg_rows;
 	const int y1 = min(h, y0 + P.seg_rows);
 	const int bc = cb >> 1;  // band column of this lane's first even/odd sample
-	constexpr int ES = SH ? 2 : 4;
+	const char *arena = P.arena + img * P.arena_img_stride + plane * P.arena_plane_stride;
+	const char *llp = (const char *)P.ll + (img * P.ll_img_stride + plane * P.ll_plane_stride) * (P.llsrc == LLSRC_S32 ? 4 : 2);
 
-	// vertical state per plane: se0 raw even row 2t-2, so4 U4'd odd row 2t-3, se3 U3'd even row 2t-4, so2 U2'd odd row 2t-5
-	int se0[NPL][8], so4[NPL][8], se3[NPL][8], so2[NPL][8];
+	// vertical state: se0 raw even row 2t-2, so4 U4'd odd row 2t-3, se3 U3'd even row 2t-4, so2 U2'd odd row 2t-5
+	int se0[8], so4[8], se3[8], so2[8];
 #pragma unroll
-	for (int p = 0; p < NPL; p++)
-#pragma unroll
-		for (int k = 0; k < 8; k++) se0[p][k] = so4[p][k] = se3[p][k] = so2[p][k] = 0;
+	for (int k = 0; k < 8; k++) se0[k] = so4[k] = se3[k] = so2[k] = 0;
 
 	const int t_begin = max((y0 >> 1) - 2, 0), t_last = (y1 + 3) >> 1;
-#pragma unroll 2
+	RawIn<SH> in;
+	load_in<SH>(in, P, arena, llp, t_begin, bc, col_ok);
+
+#pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
-		int outE[NPL][8], outO[NPL][8];
-		const int re = 2 * t, ro = 2 * t - 1;  // rows arriving now
+		int xe[8], xo[8];
+		unpack_in<SH>(in, P, plane, xe, xo);
+		load_in<SH>(in, P, arena, llp, t + 1, bc, col_ok);  // prefetch
+
 		const int r4 = 2 * t - 1, r3 = 2 * t - 2, r2 = 2 * t - 3, r1 = 2 * t - 4;
-		const bool edge_y = (r1 - 1 <= 0) || (re >= h - 1);
-#pragma unroll
-		for (int p = 0; p < NPL; p++) {
-			const int plane = NPL == 3 ? p : plane0;
-			const char *arena = P.arena + img * P.arena_img_stride + plane * P.arena_plane_stride;
-			int xe[8], xo[8];
-			{
-				int d[4], hh[4], v[4], l[4];
-				const bool e_ok = re < h;
-				const bool o_ok = ro >= 0 && ro < h;
-				const BandRef &D = P.band[0], &H = P.band[1], &V = P.band[2];
-				load4<SH>(arena + D.off + (long long)t * D.stride * ES, bc, col_ok && e_ok && bc < D.dimx, d);
-				const long long hoff = t == 1 ? (long long)P.h_row1_off : (long long)t * H.stride;
-				load4<SH>(arena + H.off + hoff * ES, bc, col_ok && e_ok && bc < H.dimx, hh);
-				load4<SH>(arena + V.off + (long long)(t - 1) * V.stride * ES, bc, col_ok && o_ok && bc < V.dimx, v);
-				if (LLSRC == LLSRC_BAND) {
-					const BandRef &L = P.lband;
-					load4<SH>(arena + L.off + (long long)(t - 1) * L.stride * ES, bc, col_ok && o_ok && bc < L.dimx, l);
-#pragma unroll
-					for (int k = 0; k < 4; k++) l[k] = TR<SH>(l[k] * P.dq[plane][3]);
-				} else if (LLSRC == LLSRC_S16) {
-					const short *lp = (const short *)P.ll + img * P.ll_img_stride + plane * P.ll_plane_stride +
-					                  (long long)(t - 1) * P.ll_pitch;
-					load4<true>((const char *)lp, bc, col_ok && o_ok && bc < (w >> 1), l);
-				} else {
-					const int *lp = (const int *)P.ll + img * P.ll_img_stride + plane * P.ll_plane_stride +
-					                (long long)(t - 1) * P.ll_pitch;
-					load4<false>((const char *)lp, bc, col_ok && o_ok && bc < (w >> 1), l);
-#pragma unroll
-					for (int k = 0; k < 4; k++) l[k] = TR<SH>(l[k]);  // (C) narrowing, wavelet2d.cpp:971-980
-				}
-				const int qd = P.dq[plane][0], qh = P.dq[plane][1], qv = P.dq[plane][2];
-#pragma unroll
-				for (int k = 0; k < 4; k++) {  // TSUQi: pBand[n] *= Quant (truncating store)
-					xe[2 * k] = TR<SH>(d[k] * qd);
-					xe[2 * k + 1] = TR<SH>(hh[k] * qh);
-					xo[2 * k] = TR<SH>(v[k] * qv);
-					xo[2 * k + 1] = l[k];
-				}
-			}
-			if (edge_y) {
-				if (r4 >= 0 && r4 < h) vU4<SH, TRANS, true>(xo, se0[p], xe, false, r4 == h - 1);
-				if (r3 >= 0 && r3 < h) vU3<SH, TRANS, true>(se0[p], so4[p], xo, r3 == 0, r3 == h - 1);
-				if (r2 >= 0 && r2 < h) vU2<SH, TRANS, true>(so4[p], se3[p], se0[p], false, r2 == h - 1);
-				if (r1 >= 0 && r1 < h) vU1<SH, TRANS, true>(se3[p], so2[p], so4[p], r1 == 0, r1 == h - 1);
-			} else {
-				vU4<SH, TRANS, false>(xo, se0[p], xe, false, false);
-				vU3<SH, TRANS, false>(se0[p], so4[p], xo, false, false);
-				vU2<SH, TRANS, false>(so4[p], se3[p], se0[p], false, false);
-				vU1<SH, TRANS, false>(se3[p], so2[p], so4[p], false, false);
-			}
-			// finished: even row r1 (se3), odd row r2 (so4)
-#pragma unroll
-			for (int k = 0; k < 8; k++) { outE[p][k] = se3[p][k]; outO[p][k] = so4[p][k]; }
-			if (edge_x) { row_inv<SH, TRANS, true>(outE[p], cb, w); row_inv<SH, TRANS, true>(outO[p], cb, w); }
-			else { row_inv<SH, TRANS, false>(outE[p], cb, w); row_inv<SH, TRANS, false>(outO[p], cb, w); }
-			// rotate
-#pragma unroll
-			for (int k = 0; k < 8; k++) { so2[p][k] = so4[p][k]; se3[p][k] = se0[p][k]; se0[p][k] = xe[k]; so4[p][k] = xo[k]; }
+		const bool edge_y = (r1 - 1 <= 0) || (2 * t >= h - 1);
+		if (edge_y) {
+			if (r4 >= 0 && r4 < h) vU4<SH, TRANS, true>(xo, se0, xe, false, r4 == h - 1);
+			if (r3 >= 0 && r3 < h) vU3<SH, TRANS, true>(se0, so4, xo, r3 == 0, r3 == h - 1);
+			if (r2 >= 0 && r2 < h) vU2<SH, TRANS, true>(so4, se3, se0, false, r2 == h - 1);
+			if (r1 >= 0 && r1 < h) vU1<SH, TRANS, true>(se3, so2, so4, r1 == 0, r1 == h - 1);
+		} else {
+			vU4<SH, TRANS, false>(xo, se0, xe, false, false);
+			vU3<SH, TRANS, false>(se0, so4, xo, false, false);
+			vU2<SH, TRANS, false>(so4, se3, se0, false, false);
+			vU1<SH, TRANS, false>(se3, so2, so4, false, false);
 		}
-		// ---- write rows r1 (even) and r2 (odd)
+		// finished: even row r1 (se3), odd row r2 (so4)
+		int oe[8], oo[8];
 #pragma unroll
-		for (int half = 0; half < 2; half++) {
-			const int row = half ? r2 : r1;
-			if (!(row >= y0 && row < y1 && lane_out)) continue;
-			if (DST == DST_S16) {
-				const int *o = half ? outO[0] : outE[0];
-				short *dp = (short *)P.dst + img * P.dst_img_stride + plane0 * P.dst_plane_stride + (long long)row * P.dst_pitch + cb;
-				uint4 pk;
-				pk.x = (unsigned)(o[0] & 0xFFFF) | ((unsigned)o[1] << 16);
-				pk.y = (unsigned)(o[2] & 0xFFFF) | ((unsigned)o[3] << 16);
-				pk.z = (unsigned)(o[4] & 0xFFFF) | ((unsigned)o[5] << 16);
-				pk.w = (unsigned)(o[6] & 0xFFFF) | ((unsigned)o[7] << 16);
-				*(uint4 *)dp = pk;
-			} else if (DST == DST_S32) {
-				const int *o = half ? outO[0] : outE[0];
-				int *dp = (int *)P.dst + img * P.dst_img_stride + plane0 * P.dst_plane_stride + (long long)row * P.dst_pitch + cb;
-				*(int4 *)dp = make_int4(o[0], o[1], o[2], o[3]);
-				*(int4 *)(dp + 4) = make_int4(o[4], o[5], o[6], o[7]);
-			} else if (DST == DST_U8_GRAY) {
-				const int *o = half ? outO[0] : outE[0];
+		for (int k = 0; k < 8; k++) { oe[k] = se3[k]; oo[k] = so4[k]; }
+		if (edge_x) { row_inv<SH, TRANS, true>(oe, cb, w); row_inv<SH, TRANS, true>(oo, cb, w); }
+		else { row_inv<SH, TRANS, false>(oe, cb, w); row_inv<SH, TRANS, false>(oo, cb, w); }
+		// rotate
+#pragma unroll
+		for (int k = 0; k < 8; k++) { so2[k] = so4[k]; se3[k] = se0[k]; se0[k] = xe[k]; so4[k] = xo[k]; }
+
+		if (DST == DST_PLANE) {
+#pragma unroll
+			for (int half = 0; half < 2; half++) {
+				const int row = half ? r2 : r1;
+				const int *o = half ? oo : oe;
+				if (!(row >= y0 && row < y1 && lane_out)) continue;
+				if (SH) {
+					short *dp = (short *)P.dst + img * P.dst_img_stride + plane * P.dst_plane_stride + (long long)row * P.dst_pitch + cb;
+					*(uint4 *)dp = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+				} else {
+					int *dp = (int *)P.dst + img * P.dst_img_stride + plane * P.dst_plane_stride + (long long)row * P.dst_pitch + cb;
+					*(int4 *)dp = make_int4(o[0], o[1], o[2], o[3]);
+					*(int4 *)(dp + 4) = make_int4(o[4], o[5], o[6], o[7]);
+				}
+			}
+		} else if (DST == DST_U8_GRAY) {
+#pragma unroll
+			for (int half = 0; half < 2; half++) {
+				const int row = half ? r2 : r1;
+				const int *o = half ? oo : oe;
+				if (!(row >= y0 && row < y1 && lane_out)) continue;
 				unsigned b[8];
 #pragma unroll
 				for (int k = 0; k < 8; k++) {  // ric.cpp:229 / :237-240
@@ -182,34 +231,55 @@ __global__ void __launch_bounds__(128) inv_level_kernel(const __grid_constant__ 
 					v = P.shift ? clip255((int)(short)(128 + ((v + 8) >> 4))) : (v + 128);
 					b[k] = (unsigned)v & 0xFF;
 				}
-				unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + plane0 * P.dst_plane_stride +
+				unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + plane * P.dst_plane_stride +
 				                    (long long)row * P.dst_pitch + cb;
-				*(uint2 *)dp = make_uint2(b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24, b[4] | b[5] << 8 | b[6] << 16 | b[7] << 24);
-			} else {
-				unsigned R[8], G[8], B[8];
+				*(uint2 *)dp = make_uint2(pack4b(b[0], b[1], b[2], b[3]), pack4b(b[4], b[5], b[6], b[7]));
+			}
+		} else {
+			// stage this plane's two rows; every third iteration (and at the end) the three warps of the
+			// group swap planes through shared memory and each converts one iteration's pixel rows
+			const int slot = (t - t_begin) % 3;
+			s_stage[grp][slot][plane][0][lane] = make_uint4(pack2(oe[0], oe[1]), pack2(oe[2], oe[3]), pack2(oe[4], oe[5]), pack2(oe[6], oe[7]));
+			s_stage[grp][slot][plane][1][lane] = make_uint4(pack2(oo[0], oo[1]), pack2(oo[2], oo[3]), pack2(oo[4], oo[5]), pack2(oo[6], oo[7]));
+			if (slot == 2 || t == t_last) {
+				asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory");
+				const int my = plane;  // this warp converts the rows staged in slot `plane`
+				if (my <= slot) {
+					const int tt = t - (slot - my);
 #pragma unroll
-				for (int k = 0; k < 8; k++) {  // YCoCgtoRGB<shift>, ric.cpp:93-112 (planes 0 Co, 1 Cg, 2 Y)
-					int co = half ? outO[0][k] : outE[0][k];
-					int cg = half ? outO[NPL > 1 ? 1 : 0][k] : outE[NPL > 1 ? 1 : 0][k];
-					int y = half ? outO[NPL > 2 ? 2 : 0][k] : outE[NPL > 2 ? 2 : 0][k];
-					if (P.shift) {
-						co = (int)(short)((co + 4) >> 3);
-						cg = (int)(short)((cg + 4) >> 3);
-						y = (int)(short)((y + 8) >> 4);
+					for (int half = 0; half < 2; half++) {
+						const int row = half ? 2 * tt - 3 : 2 * tt - 4;
+						if (!(row >= y0 && row < y1 && lane_out)) continue;
+						const uint4 c0 = s_stage[grp][my][0][half][lane], c1 = s_stage[grp][my][1][half][lane],
+						            c2 = s_stage[grp][my][2][half][lane];
+						unsigned R[8], G[8], B[8];
+#pragma unroll
+						for (int k = 0; k < 8; k++) {  // YCoCgtoRGB<shift>, ric.cpp:93-112 (planes 0 Co, 1 Cg, 2 Y)
+							const unsigned w0 = k < 2 ? c0.x : k < 4 ? c0.y : k < 6 ? c0.z : c0.w;
+							const unsigned w1 = k < 2 ? c1.x : k < 4 ? c1.y : k < 6 ? c1.z : c1.w;
+							const unsigned w2 = k < 2 ? c2.x : k < 4 ? c2.y : k < 6 ? c2.z : c2.w;
+							int co = (k & 1) ? (int)w0 >> 16 : (int)(short)(w0 & 0xFFFF);
+							int cg = (k & 1) ? (int)w1 >> 16 : (int)(short)(w1 & 0xFFFF);
+							int y = (k & 1) ? (int)w2 >> 16 : (int)(short)(w2 & 0xFFFF);
+							if (P.shift) {
+								co = (int)(short)((co + 4) >> 3);
+								cg = (int)(short)((cg + 4) >> 3);
+								y = (int)(short)((y + 8) >> 4);
+							}
+							y = (int)(short)(y - ((cg >> 1) - 128));
+							cg = (int)(short)(cg + y);
+							y = (int)(short)(y - (co >> 1));
+							co = (int)(short)(co + y);
+							if (P.shift) { co = clip255(co); cg = clip255(cg); y = clip255(y); }
+							R[k] = (unsigned)co & 0xFF; G[k] = (unsigned)cg & 0xFF; B[k] = (unsigned)y & 0xFF;
+						}
+						unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + (long long)row * P.dst_pitch + cb;
+						*(uint2 *)dp = make_uint2(pack4b(R[0], R[1], R[2], R[3]), pack4b(R[4], R[5], R[6], R[7]));
+						*(uint2 *)(dp + P.dst_plane_stride) = make_uint2(pack4b(G[0], G[1], G[2], G[3]), pack4b(G[4], G[5], G[6], G[7]));
+						*(uint2 *)(dp + 2 * P.dst_plane_stride) = make_uint2(pack4b(B[0], B[1], B[2], B[3]), pack4b(B[4], B[5], B[6], B[7]));
 					}
-					y = (int)(short)(y - ((cg >> 1) - 128));
-					cg = (int)(short)(cg + y);
-					y = (int)(short)(y - (co >> 1));
-					co = (int)(short)(co + y);
-					if (P.shift) { co = clip255(co); cg = clip255(cg); y = clip255(y); }
-					R[k] = (unsigned)co & 0xFF; G[k] = (unsigned)cg & 0xFF; B[k] = (unsigned)y & 0xFF;
 				}
-				unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + (long long)row * P.dst_pitch + cb;
-				*(uint2 *)dp = make_uint2(R[0] | R[1] << 8 | R[2] << 16 | R[3] << 24, R[4] | R[5] << 8 | R[6] << 16 | R[7] << 24);
-				*(uint2 *)(dp + P.dst_plane_stride) =
-				    make_uint2(G[0] | G[1] << 8 | G[2] << 16 | G[3] << 24, G[4] | G[5] << 8 | G[6] << 16 | G[7] << 24);
-				*(uint2 *)(dp + 2 * P.dst_plane_stride) =
-				    make_uint2(B[0] | B[1] << 8 | B[2] << 16 | B[3] << 24, B[4] | B[5] << 8 | B[6] << 16 | B[7] << 24);
+				asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory");
 			}
 		}
 	}
