@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode transform/quant stage throughput (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle/_ref)
+
+A step = the hot path over one batch per GPU: encode stage (colour + 5-level 9/7 DWT + encode
+quantiser, u8 pixels -> quantised band arenas) followed by the decode stage (dequantise + inverse
+DWT + inverse colour, signed band arenas -> u8 pixels) of `--batch` synthetic 3840x2160 RGB images
+(BASELINE.json configs[1] shape, batched as configs[3] does; images are independent, so ranks
+shard the batch with no data-path collective: weak scaling).  value = Mpixel/s, every image
+counted once per direction, whole job.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W_, H_, CH_, LEVELS_, Q_ = 3840, 2160, 3, 5, 9
+ALG_BYTES_PER_SAMPLE = 3.0        # encode 1 B u8 in + 2 B s16 out; decode 2 B in + 1 B out
+L0_FWD_BYTES_PER_SAMPLE = 2.5     # level-0 forward kernel alone: 1 B u8 in + 3/4 * 2 B quantised HF bands out
+L0_INV_BYTES_PER_SAMPLE = 2.5     # level-0 inverse kernel alone: 3/4 * 2 B bands in + 1 B u8 out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--q", type=int, default=Q_)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.004)
+        except Exception as e:  # NVML missing: report that rather than fail the bench
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        s = sorted(self.sm)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_stage(n_images, threads, q):
+    """Times the reference's own CPU implementation (oracle/_ref/libric_ref.so) of the stage."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import refbind
+    from rududu_image_codec_b200.synth import synth_image
+    if not refbind.available():
+        return None
+    img = np.ascontiguousarray(synth_image(0, W_, H_, CH_))
+    L = refbind.lib()
+    t_enc = L.ref_bench_stage(img.ctypes.data, W_, H_, CH_, q, 0, LEVELS_, LEVELS_ - 4, n_images, threads, 0)
+    t_dec = L.ref_bench_stage(img.ctypes.data, W_, H_, CH_, q, 0, LEVELS_, LEVELS_ - 4, n_images, threads, 1)
+    return t_enc, t_dec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_images = threads  # bounded sample: one 4K RGB image per host thread per step
+    r = cpu_reference_stage(n_images, threads, args.q)  # also the first warm-up
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libric_ref.so not built"}))
+        return
+    for _ in range(max(args.warmup - 1, 0)):
+        cpu_reference_stage(n_images, threads, args.q)
+    t0 = time.perf_counter()
+    te = td = 0.0
+    for _ in range(args.steps):
+        a, b = cpu_reference_stage(n_images, threads, args.q)
+        te += a
+        td += b
+    wall = time.perf_counter() - t0
+    t = te + td
+    mpix = 2.0 * n_images * args.steps * W_ * H_ / t / 1e6
+    sample = "%d images (one per host thread) of 3840x2160 RGB per step, stage time = busiest thread" % n_images
+    line = {
+        "impl": "reference", "metric": "encode+decode transform+quant stage throughput", "value": mpix,
+        "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16", "data": "synthetic",
+        "config": {"workload": "3840x2160 RGB, 5-level cdf97, q=%d, encode+decode stage" % args.q,
+                   "images_per_step": n_images, "host_threads": threads},
+        "encode_mpix_s": n_images * args.steps * W_ * H_ / te / 1e6,
+        "decode_mpix_s": n_images * args.steps * W_ * H_ / td / 1e6,
+        "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line))
+
+
+def unfold_arenas_(ctx, arenas, n):
+    """Folded encode output -> signed coefficients (what the host entropy decoder leaves in the
+    bands): u2s_ (src/lib/utils.h:101-105) on every D/H/V band, INSIGNIF_BLOCK markers -> 0.  Setup
+    plumbing for the decode input, done with torch ops on the device (not timed)."""
+    import torch
+    for img in range(n):
+        for p in range(ctx.channels):
+            base = img * ctx.image_arena_bytes + p * ctx.arena_bytes
+            for i in range(ctx.nbands - 1):
+                f = ctx.band(i)
+                nbytes = f["stride"] * f["dimy"] * f["size"]
+                raw = arenas[base + f["offset"]: base + f["offset"] + nbytes]
+                if f["is_int"]:
+                    v = raw.view(torch.int32)
+                    u = v
+                else:
+                    v = raw.view(torch.int16)
+                    u = v.to(torch.int32) & 0xFFFF
+                mag = u >> 1
+                out = torch.where((u & 1) != 0, -mag, mag)
+                out = torch.where(v == -0x8000, torch.zeros_like(out), out)
+                v.copy_(out.to(v.dtype))
+
+
+def pinned_array(ctx_lib, nbytes):
+    import numpy as np
+    p = ctypes.c_void_p()
+    rc = ctx_lib.ric_host_alloc(ctypes.byref(p), nbytes)
+    if rc != 0:
+        raise RuntimeError("ric_host_alloc failed")
+    buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+    return np.frombuffer(buf, dtype=np.uint8), p
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from rududu_image_codec_b200 import capi
+    from rududu_image_codec_b200.synth import synth_image
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, q = args.batch, args.q
+
+    ctx = capi.Context(W_, H_, CH_, LEVELS_, max_batch=B, device=local)
+    pitch = W_  # multiple of 8: dense rows
+    distinct = min(B, 4)
+    host_imgs = np.stack([synth_image(rank * distinct + i, W_, H_, CH_) for i in range(distinct)])
+    host_batch = np.ascontiguousarray(host_imgs[np.arange(B) % distinct])
+    src = torch.from_numpy(host_batch).to(dev)
+    arenas = torch.zeros(B * ctx.image_arena_bytes + 64, dtype=torch.uint8, device=dev)
+    dec_in = torch.zeros_like(arenas)
+    dst = torch.zeros((B, CH_, H_, pitch), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        ctx.encode_u8_device(src.data_ptr(), pitch, B, q, arenas.data_ptr(), st)
+        ctx.decode_u8_device(dec_in.data_ptr(), B, q, dst.data_ptr(), pitch, st)
+
+    # decode input = signed view of the encode output (setup, untimed)
+    ctx.encode_u8_device(src.data_ptr(), pitch, B, q, arenas.data_ptr(), st)
+    torch.cuda.synchronize()
+    dec_in.copy_(arenas)
+    unfold_arenas_(ctx, dec_in, distinct)
+    per = ctx.image_arena_bytes
+    for i in range(distinct, B):
+        dec_in[i * per:(i + 1) * per].copy_(dec_in[(i % distinct) * per:((i % distinct) + 1) * per])
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    ctx.set_profiling(True)
+    e0, e1, em = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    enc_ms = dec_ms = 0.0
+    barrier()
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    total_ms = e0.elapsed_time(e1)
+    lt_enc, lt_dec = ctx.level_times(0), ctx.level_times(1)  # last timed step, per launch
+    enc_ms, dec_ms = sum(lt_enc), sum(lt_dec)
+    ctx.set_profiling(False)
+    sampler.join(timeout=2)
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    pixels_per_step = world * B * W_ * H_
+    value = 2.0 * pixels_per_step * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C ABI calls (pinned host memory, copies inside) ----
+    L = capi.lib()
+    h_src, p1 = pinned_array(L, host_batch.nbytes)
+    h_ar, p2 = pinned_array(L, B * ctx.image_arena_bytes)
+    h_dec_in, p3 = pinned_array(L, B * ctx.image_arena_bytes)
+    h_dst, p4 = pinned_array(L, host_batch.nbytes)
+    h_src[:] = host_batch.reshape(-1)
+    h_dec_in[:] = dec_in[:B * ctx.image_arena_bytes].cpu().numpy()
+    ctx.encode_u8(h_src, q, out=h_ar)
+    ctx.decode_u8(h_dec_in, B, q, out=h_dst)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ctx.encode_u8(h_src, q, out=h_ar)
+        ctx.decode_u8(h_dec_in, B, q, out=h_dst)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = 2.0 * pixels_per_step * args.e2e_steps / float(te.item()) / 1e6
+    h2d = host_batch.nbytes + B * ctx.image_arena_bytes
+    d2h = B * ctx.image_arena_bytes + host_batch.nbytes
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        S = B * W_ * H_ * CH_  # samples per GPU per step
+        k_ms = lt_enc[0]       # dominant kernel: level-0 forward (colour + DWT + quantiser), finest level first
+        achieved = L0_FWD_BYTES_PER_SAMPLE * S / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "encode+decode transform+quant stage throughput", "value": value, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+            "config": {"workload": "3840x2160 RGB (BASELINE configs[1] shape), 5-level cdf97, q=%d, batch %d images per GPU, "
+                                   "encode stage + decode stage per step" % (q, B),
+                       "batch_per_gpu": B, "distinct_images_per_gpu": distinct,
+                       "l2": "inputs larger than L2 (%.0f MB read+written per step)" % ((h2d + d2h) / 1e6),
+                       "sharding": "independent images per rank, no collective"},
+            "encode_mpix_s": world * B * W_ * H_ / (enc_ms * 1e-3) / 1e6,
+            "decode_mpix_s": world * B * W_ * H_ / (dec_ms * 1e-3) / 1e6,
+            "stage": {"encode_ms": enc_ms, "decode_ms": dec_ms,
+                      "encode_alg_gbs": ALG_BYTES_PER_SAMPLE * S / (enc_ms * 1e-3) / 1e9,
+                      "decode_alg_gbs": ALG_BYTES_PER_SAMPLE * S / (dec_ms * 1e-3) / 1e9,
+                      "encode_frac": ALG_BYTES_PER_SAMPLE * S / (enc_ms * 1e-3) / 1e9 / peak,
+                      "decode_frac": ALG_BYTES_PER_SAMPLE * S / (dec_ms * 1e-3) / 1e9 / peak,
+                      "level_ms_encode": lt_enc, "level_ms_decode": lt_dec},
+            "roofline": {"bound": "hbm", "kernel": "fwd_level_kernel<short, cdf97, SRC_U8_RGB> (level 0)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": L0_FWD_BYTES_PER_SAMPLE * S},
+            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": args.e2e_steps, "api": "ric_encode_u8 + ric_decode_u8 (pinned host buffers)"},
+            "gpu_launches": 2 * ctx.nlev * args.steps,
+            "clocks": sampler.result(),
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("fwd_level0_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            r = cpu_reference_stage(threads, threads, q)
+            if r is not None:
+                te_, td_ = r
+                line["cpu_baseline"] = {
+                    "value": 2.0 * threads * W_ * H_ / (te_ + td_) / 1e6, "unit": "Mpixel/s", "cores": threads,
+                    "kind": "reference",
+                    "sample": "%d images (one per host thread) of the same 3840x2160 RGB workload, one pass" % threads,
+                    "encode_mpix_s": threads * W_ * H_ / te_ / 1e6, "decode_mpix_s": threads * W_ * H_ / td_ / 1e6}
+        print(json.dumps(line))
+    for p in (p1, p2, p3, p4):
+        L.ric_host_free(p)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.gpus > 1 and "RANK" not in os.environ:  # convenience: re-launch under torchrun
+        port = str(29500 + os.getpid() % 2000)
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+                                   "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

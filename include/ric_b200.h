@@ -100,6 +100,13 @@ int ric_decode_u8_device(ric_ctx *ctx, const void *d_arenas, int n, int q, uint8
 /* number of kernel launches the last *_device call enqueued (for bench accounting) */
 int ric_last_launch_count(const ric_ctx *ctx);
 
+/* Optional per-launch timing: when on, a CUDA event is recorded on the launching stream around every
+ * level kernel of the *_device calls.  ric_get_level_times waits for the last recorded call of the
+ * given direction (0 encode: finest level first; 1 decode: coarsest level first) and writes one
+ * duration per launch in milliseconds; returns the number of launches (<= RIC_MAX_LEVELS) or < 0. */
+int ric_set_profiling(ric_ctx *ctx, int on);
+int ric_get_level_times(ric_ctx *ctx, int direction, float *ms, int cap);
+
 /* ---- plane-level entry points mirroring the reference class API (HOST buffers) -------------------
  * One plane at a time on batch slot 0, like a CWavelet2D object:
  * ric_transform:   CWavelet2D::Transform<short>(pImage, Stride, t)  wavelet2d.cpp:926.

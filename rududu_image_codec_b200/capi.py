@@ -21,7 +21,7 @@ EXPORTS = [
     "ric_create", "ric_destroy", "ric_get_info", "ric_get_band", "ric_last_error", "ric_quants",
     "ric_plane_quant", "ric_encode_u8", "ric_decode_u8", "ric_encode_u8_device", "ric_decode_u8_device",
     "ric_last_launch_count", "ric_transform", "ric_quant", "ric_tsuq", "ric_tsuqi", "ric_transform_inv",
-    "ric_host_alloc", "ric_host_free",
+    "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times",
 ]
 
 
@@ -74,6 +74,8 @@ def lib():
         L.ric_transform_inv.argtypes = [vp, vp, vp, i]
         L.ric_host_alloc.argtypes = [C.POINTER(vp), sz]
         L.ric_host_free.argtypes = [vp]
+        L.ric_set_profiling.argtypes = [vp, i]
+        L.ric_get_level_times.argtypes = [vp, i, C.POINTER(C.c_float), i]
         _lib = L
     return _lib
 
@@ -167,6 +169,17 @@ class Context:
 
     def decode_u8_device(self, d_arenas, n, q, d_dst, pitch, stream=0):
         _check(self.L.ric_decode_u8_device(self.h, d_arenas, n, q, d_dst, pitch, stream))
+
+    def set_profiling(self, on=True):
+        _check(self.L.ric_set_profiling(self.h, int(on)))
+
+    def level_times(self, direction):
+        """Per-launch durations (ms) of the last encode (0) / decode (1) *_device call."""
+        buf = (C.c_float * MAX_LEVELS)()
+        n = self.L.ric_get_level_times(self.h, direction, buf, MAX_LEVELS)
+        if n < 0:
+            _check(n)
+        return [buf[k] for k in range(n)]
 
     def last_launch_count(self):
         return self.L.ric_last_launch_count(self.h)

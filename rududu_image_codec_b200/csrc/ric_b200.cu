@@ -49,6 +49,9 @@ struct ric_ctx {
 	int ll_es[RIC_MAX_LEVELS];
 	unsigned *d_count;
 	int launches;
+	int profiling;                       // record CUDA events around every level launch
+	cudaEvent_t ev[2][RIC_MAX_LEVELS + 1];  // [direction][launch boundary]
+	int ev_n[2];
 	int target_warps;
 };
 
@@ -208,6 +211,9 @@ int ric_destroy(ric_ctx *c)
 	cudaFree(c->d_flags);
 	cudaFree(c->d_plane);
 	cudaFree(c->d_count);
+	for (int d = 0; d < 2; d++)
+		for (int i = 0; i <= RIC_MAX_LEVELS; i++)
+			if (c->ev[d][i]) cudaEventDestroy(c->ev[d][i]);
 	for (int i = 0; i < RIC_MAX_LEVELS; i++) cudaFree(c->d_ll[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -266,6 +272,8 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 		CKD(cudaMemset(c->d_ll[i], 0, bytes));
 	}
 	CKD(cudaMalloc(&c->d_count, sizeof(unsigned)));
+	for (int d = 0; d < 2; d++)
+		for (int i = 0; i <= g.nlev; i++) CKD(cudaEventCreate(&c->ev[d][i]));
 	CKD(cudaDeviceSynchronize());
 #undef CKD
 	*out = c;
@@ -292,6 +300,24 @@ int ric_get_band(const ric_ctx *c, int id, ric_band_info *info)
 }
 
 int ric_last_launch_count(const ric_ctx *c) { return c ? c->launches : 0; }
+
+int ric_set_profiling(ric_ctx *c, int on)
+{
+	if (!c) return set_err(RIC_E_ARG, "ric_set_profiling: null");
+	c->profiling = on != 0;
+	return RIC_OK;
+}
+
+int ric_get_level_times(ric_ctx *c, int direction, float *ms, int cap)
+{
+	if (!c || !ms || direction < 0 || direction > 1) return set_err(RIC_E_ARG, "ric_get_level_times: bad argument");
+	const int n = c->ev_n[direction];
+	if (n == 0 || cap < n) return set_err(RIC_E_ARG, "ric_get_level_times: nothing recorded (enable ric_set_profiling) or cap too small");
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventSynchronize(c->ev[direction][n]));
+	for (int i = 0; i < n; i++) CK(cudaEventElapsedTime(&ms[i], c->ev[direction][i], c->ev[direction][i + 1]));
+	return n;
+}
 
 int ric_host_alloc(void **p, size_t bytes)
 {
@@ -320,6 +346,8 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 {
 	const HostGeom &g = c->g;
 	c->launches = 0;
+	c->ev_n[0] = 0;
+	if (c->profiling) { CK(cudaEventRecord(c->ev[0][0], st)); }
 	for (int lv = 0; lv < g.nlev; lv++) {
 		FwdParams P;
 		memset(&P, 0, sizeof P);
@@ -385,6 +413,7 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 		fn<<<grid, wpb * 32, 0, st>>>(P);
 		CK(cudaGetLastError());
 		c->launches++;
+		if (c->profiling) { CK(cudaEventRecord(c->ev[0][c->launches], st)); c->ev_n[0] = c->launches; }
 	}
 	return RIC_OK;
 }
@@ -396,6 +425,8 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 {
 	const HostGeom &g = c->g;
 	c->launches = 0;
+	c->ev_n[1] = 0;
+	if (c->profiling) { CK(cudaEventRecord(c->ev[1][0], st)); }
 	for (int lv = g.nlev - 1; lv >= 0; lv--) {
 		InvParams P;
 		memset(&P, 0, sizeof P);
@@ -450,6 +481,7 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		}
 		CK(cudaGetLastError());
 		c->launches++;
+		if (c->profiling) { CK(cudaEventRecord(c->ev[1][c->launches], st)); c->ev_n[1] = c->launches; }
 	}
 	return RIC_OK;
 }
