@@ -176,6 +176,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from rududu_image_codec_b200 import capi
+    from rududu_image_codec_b200.sharding import max_over_ranks, shard
     from rududu_image_codec_b200.synth import synth_image
 
     if not torch.cuda.is_available():
@@ -192,7 +193,8 @@ def run_ours(args):
     ctx = capi.Context(W_, H_, CH_, LEVELS_, max_batch=B, device=local)
     pitch = W_  # multiple of 8: dense rows
     distinct = min(B, 4)
-    host_imgs = np.stack([synth_image(rank * distinct + i, W_, H_, CH_) for i in range(distinct)])
+    first, _ = shard(world * B, rank, world)  # this rank's slice of the global batch (weak scaling: B each)
+    host_imgs = np.stack([synth_image(first + i, W_, H_, CH_) for i in range(distinct)])
     host_batch = np.ascontiguousarray(host_imgs[np.arange(B) % distinct])
     src = torch.from_numpy(host_batch).to(dev)
     arenas = torch.zeros(B * ctx.image_arena_bytes + 64, dtype=torch.uint8, device=dev)
@@ -239,10 +241,7 @@ def run_ours(args):
     ctx.set_profiling(False)
     sampler.join(timeout=2)
 
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms, dev)
     pixels_per_step = world * B * W_ * H_
     value = 2.0 * pixels_per_step * args.steps / (total_ms * 1e-3) / 1e6
 
@@ -263,10 +262,7 @@ def run_ours(args):
         ctx.decode_u8(h_dec_in, B, q, out=h_dst)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = 2.0 * pixels_per_step * args.e2e_steps / float(te.item()) / 1e6
+    e2e_val = 2.0 * pixels_per_step * args.e2e_steps / max_over_ranks(e2e_s, dev) / 1e6
     h2d = host_batch.nbytes + B * ctx.image_arena_bytes
     d2h = B * ctx.image_arena_bytes + host_batch.nbytes
 

@@ -1,0 +1,184 @@
+// rududu_b200/wavelet2d.h -- the reference's C++ class API for the transform+quant path,
+// re-created on top of the C ABI (ric_b200.h).  Header-only; link with -lrududu_b200.
+//
+// What it mirrors (names, argument meaning, ownership):
+//   enum trans / cmode                     src/lib/utils.h:27-28
+//   enum band_t, ALIGN                     src/lib/band.h:33-35
+//   class CBand (public fields)            src/lib/band.h:37-161
+//   class CBandCodec::buildTree            src/lib/bandcodec.h:42   (here: CWavelet2D::QuantBands)
+//   class CWavelet2D                       src/lib/wavelet2d.h:27-88
+//        CWavelet2D(x, y, level, level_chg, Align), SetWeight, Transform<short>, TransformI<short>,
+//        TSUQ, TSUQi, public DBand/HBand/VBand/LBand, pLow/pHigh chain
+// Differences a maintainer must know (INTEGRATION.md has the full list):
+//   * CodeBand = {quantiser half} + {entropy half}.  The quantiser half (buildTree x3 + LL TSUQ,
+//     wavelet2d.cpp:110-126) is QuantBands(Quant, lambda) here and runs on the GPU; the entropy half
+//     (CBandCodec::pred/tree) stays the reference's host code and reads the same pBand buffers.
+//   * Transform() leaves the caller's plane untouched (the reference destroys it).
+//   * Band buffers of all levels live in ONE pinned host arena owned by the top-level object; every
+//     CBand::pBand points into it with the reference's DimXAlign stride and 32-byte alignment.
+//   * Errors: the reference has none; here a failing C-ABI call throws std::runtime_error with
+//     ric_last_error() (never across the C ABI itself).
+// The namespace is rududu_b200 so that the shim can be linked next to the reference library in
+// tests; a drop-in build adds `namespace rududu = rududu_b200;`.
+#pragma once
+#include <stdexcept>
+#include <string>
+
+#include "../ric_b200.h"
+
+namespace rududu_b200 {
+
+typedef enum cmode { encode, decode } cmode;
+typedef enum trans { cdf97 = 0, cdf53 = 1, haar = 2 } trans;
+typedef enum band_t { sshort, sint } band_t;
+#ifndef ALIGN
+#define ALIGN 32
+#endif
+
+class CBand {
+public:
+	unsigned int DimX = 0, DimY = 0, DimXAlign = 0, BandSize = 0;
+	int Max = 0, Min = 0;
+	unsigned int Dist = 0, Count = 0;
+	float Weight = 1.f;
+	CBand *pParent = 0, *pChild = 0, *pNeighbor[3] = {0, 0, 0};
+	char *pBand = 0;  // points into the owning CWavelet2D's pinned arena
+	band_t type = sshort;
+};
+
+typedef CBand CBandCodec;  // the entropy half lives in the reference; the data members are CBand's
+
+class CWavelet2D {
+public:
+	CWavelet2D(int x, int y, int level, int level_chg = 0, int Align = ALIGN, int device = 0)
+	    : DimX(x), DimY(y), levels_(level), level_chg_(level_chg), align_(Align), device_(device)
+	{
+		ctx_[0] = ctx_[1] = 0;
+		arena_ = 0;
+		ric_ctx *c = ctx(cdf97);
+		ric_info inf;
+		check(ric_get_info(c, &inf));
+		nlev_ = inf.nlev;
+		arena_bytes_ = inf.arena_bytes;
+		void *p = 0;
+		check(ric_host_alloc(&p, arena_bytes_));
+		arena_ = (char *)p;
+		build_chain(c);
+	}
+	~CWavelet2D()
+	{
+		for (CWavelet2D *w = pLow; w;) { CWavelet2D *n = w->pLow; w->pLow = 0; delete w; w = n; }
+		if (!pHigh) {
+			if (arena_) ric_host_free(arena_);
+			for (int i = 0; i < 2; i++)
+				if (ctx_[i]) ric_destroy(ctx_[i]);
+		}
+	}
+
+	// CWavelet2D::SetWeight, wavelet2d.cpp:1009-1032 (weights come from the C ABI's band table)
+	void SetWeight(trans t, float baseWeight = 1.f)
+	{
+		if (baseWeight != 1.f) throw std::runtime_error("rududu_b200: baseWeight != 1 unsupported");
+		trans_ = t;
+		ric_ctx *c = ctx(t);
+		int id = 0;
+		for (CWavelet2D *w = this; w; w = w->pLow, id += 3) {
+			ric_band_info b;
+			check(ric_get_band(c, id, &b)); w->DBand.Weight = b.weight;
+			check(ric_get_band(c, id + 1, &b)); w->HBand.Weight = b.weight;
+			check(ric_get_band(c, id + 2, &b)); w->VBand.Weight = b.weight;
+			if (!w->pLow) { check(ric_get_band(c, id + 3, &b)); w->LBand.Weight = b.weight; }
+		}
+	}
+
+	// wavelet2d.cpp:926-958.  pImage: top-left of a DimX x DimY short plane (left untouched).
+	template <class C>
+	void Transform(C *pImage, int Stride, trans t)
+	{
+		static_assert(sizeof(C) == 2, "only Transform<short> exists in the reference (wavelet2d.cpp:958)");
+		trans_ = t;
+		check(ric_transform(ctx(t), (const int16_t *)pImage, Stride, arena_));
+	}
+
+	// wavelet2d.cpp:960-992.  pImage is the ONE-PAST-END pointer of the output plane, as in the
+	// reference (ric.cpp:216,220,225 pass data() + W*H*(c+1)).
+	template <class C>
+	void TransformI(C *pImage, int Stride, trans t)
+	{
+		static_assert(sizeof(C) == 2, "only TransformI<short> exists in the reference (wavelet2d.cpp:992)");
+		trans_ = t;
+		check(ric_transform_inv(ctx(t), arena_, (int16_t *)pImage - (size_t)Stride * DimY, Stride));
+	}
+
+	// The quantiser half of CodeBand (wavelet2d.cpp:110-126): buildTree on the D/H/V chains and
+	// TSUQ(Quant, 0.5) on the LL band, on the coefficients the last Transform() left on the GPU.
+	// Afterwards the bands hold exactly what CBandCodec::pred / tree<encode> expect.
+	void QuantBands(int Quant, int lambda) { check(ric_quant(ctx(trans_), Quant, lambda, arena_)); }
+
+	// wavelet2d.cpp:224-246 / :248-268
+	unsigned int TSUQ(int Quant, float Thres)
+	{
+		unsigned n = 0;
+		check(ric_tsuq(ctx(trans_), Quant, Thres, arena_, &n));
+		return n;
+	}
+	void TSUQi(int Quant) { check(ric_tsuqi(ctx(trans_), Quant, arena_)); }
+
+	CBandCodec DBand, HBand, VBand, LBand;
+	CWavelet2D *pLow = 0, *pHigh = 0;
+	int DimX, DimY;
+
+	char *arena() const { return arena_; }
+	size_t arena_bytes() const { return arena_bytes_; }
+
+private:
+	CWavelet2D(CWavelet2D *high, int x, int y) : pHigh(high), DimX(x), DimY(y) { ctx_[0] = ctx_[1] = 0; arena_ = 0; }
+
+	static void check(int rc)
+	{
+		if (rc < 0) throw std::runtime_error(std::string("rududu_b200: ") + ric_last_error());
+	}
+
+	CWavelet2D *top() { CWavelet2D *w = this; while (w->pHigh) w = w->pHigh; return w; }
+
+	ric_ctx *ctx(trans t)
+	{
+		CWavelet2D *T = top();
+		if (t != cdf97 && t != cdf53) throw std::runtime_error("rududu_b200: only cdf97 / cdf53 run on the GPU");
+		if (!T->ctx_[t]) check(ric_create(&T->ctx_[t], T->device_, T->DimX, T->DimY, 1, T->levels_, T->level_chg_, T->align_, t, 1));
+		return T->ctx_[t];
+	}
+
+	void fill(CBand &b, ric_ctx *c, int id)
+	{
+		ric_band_info i;
+		check(ric_get_band(c, id, &i));
+		b.DimX = i.dimx; b.DimY = i.dimy; b.DimXAlign = i.stride; b.BandSize = i.stride * i.dimy;
+		b.Weight = i.weight; b.type = i.is_int ? sint : sshort;
+		b.pBand = top()->arena_ + i.offset;
+	}
+
+	void build_chain(ric_ctx *c)
+	{
+		CWavelet2D *w = this;
+		for (int lv = 0; lv < nlev_; lv++) {
+			fill(w->DBand, c, 3 * lv); fill(w->HBand, c, 3 * lv + 1); fill(w->VBand, c, 3 * lv + 2);
+			if (w->pHigh) {  // wavelet2d.cpp:54-59
+				w->DBand.pChild = &w->pHigh->DBand; w->pHigh->DBand.pParent = &w->DBand;
+				w->HBand.pChild = &w->pHigh->HBand; w->pHigh->HBand.pParent = &w->HBand;
+				w->VBand.pChild = &w->pHigh->VBand; w->pHigh->VBand.pParent = &w->VBand;
+			}
+			if (lv == nlev_ - 1) { fill(w->LBand, c, 3 * nlev_); break; }
+			w->pLow = new CWavelet2D(w, w->DimX >> 1, w->DimY >> 1);
+			w = w->pLow;
+		}
+	}
+
+	ric_ctx *ctx_[2];
+	char *arena_;
+	size_t arena_bytes_ = 0;
+	int levels_ = 0, level_chg_ = 0, align_ = ALIGN, device_ = 0, nlev_ = 0;
+	trans trans_ = cdf97;
+};
+
+}  // namespace rududu_b200

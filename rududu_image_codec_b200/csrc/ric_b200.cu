@@ -164,6 +164,19 @@ __global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int 
 
 // ---------------------------------------------------------------------------------------------
 
+static void fill_qb(QuantBand &q, int Quant, int lambda, float weight, int is_int)
+{
+	HostQuantBand hq;
+	make_quant_band(hq, Quant, lambda, weight, is_int);
+	q.Q = hq.Q; q.iQ = hq.iQ; q.T = hq.T; q.Te = hq.Te;
+	q.fast = hq.Q >= 1 && hq.Q <= (is_int ? 32767 : 16383);
+	for (int i = 0; i < 32; i++) q.kthr[i] = 0x7fffffff;
+	for (int i = 0; i < 16; i++) {
+		q.thr[i] = hq.thr[i];
+		if (q.fast) q.kthr[i] = hq.thr[i] << 4;
+	}
+}
+
 static BandRef band_ref(const HostGeom &g, int id)
 {
 	BandRef r;
@@ -396,11 +409,7 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 			for (int cls = 0; cls < 2; cls++) {
 				const int p = cls_plane[cls];
 				for (int o = 0; o < 3; o++) {
-					HostQuantBand hq;
-					make_quant_band(hq, Quant[p], lambda[p], g.band[3 * lv + o].weight, g.lev_int[lv]);
-					QuantBand &q = P.qb[cls][o];
-					q.Q = hq.Q; q.iQ = hq.iQ; q.T = hq.T; q.Te = hq.Te;
-					for (int i = 0; i < 16; i++) q.thr[i] = hq.thr[i];
+					fill_qb(P.qb[cls][o], Quant[p], lambda[p], g.band[3 * lv + o].weight, g.lev_int[lv]);
 				}
 				make_tsuq(Quant[p], 0.5f, g.band[3 * g.nlev].weight, g.lev_int[g.nlev - 1], &P.llQ[cls], &P.lliQ[cls], &P.llT[cls]);
 			}
@@ -604,11 +613,7 @@ int ric_quant(ric_ctx *c, int Quant, int lambda, void *arena)
 		for (int o = 0; o < 3; o++) {
 			P.band[o] = band_ref(g, 3 * lv + o);
 			if (lv > 0) P.child[o] = band_ref(g, 3 * (lv - 1) + o);
-			HostQuantBand hq;
-			make_quant_band(hq, Quant, lambda, g.band[3 * lv + o].weight, g.lev_int[lv]);
-			QuantBand &q = P.qb[o];
-			q.Q = hq.Q; q.iQ = hq.iQ; q.T = hq.T; q.Te = hq.Te;
-			for (int i = 0; i < 16; i++) q.thr[i] = hq.thr[i];
+			fill_qb(P.qb[o], Quant, lambda, g.band[3 * lv + o].weight, g.lev_int[lv]);
 			maxblk = std::max(maxblk, P.band[o].fl_bw * ((P.band[o].dimy + 3) / 4));
 		}
 		dim3 grid((maxblk + 127) / 128, 3);

@@ -106,104 +106,119 @@ template <bool SH, int TRANS>
 __device__ __forceinline__ int iU1_last(int x, int l) { return TRANS == T97 ? TR<SH>(x + 3 * l) : TR<SH>(x + l); }
 
 // ---- horizontal passes on the 8 columns a lane holds (cb = absolute column of v[0], even).
-// Neighbours across lanes come from warp shuffles.  EDGE selects the absolute-coordinate edge
-// formulas (column 0 and column w-1); interior strips instantiate EDGE=false.
-template <bool SH, int TRANS, bool EDGE>
-__device__ __forceinline__ void row_fwd(int (&v)[8], int cb, int w)
+// Neighbours across lanes come from warp shuffles.  Every element is first computed with the
+// interior formula; strips that contain column 0 or column w-1 (edge_x, warp-uniform) then
+// overwrite those two elements with the absolute-coordinate edge formulas of the reference
+// (the values they replace were never used by another step).
+// NT (forward only): "no truncation" -- for rows lifted straight from 8-bit pixels (|x| <= 2048)
+// no intermediate of the four steps can leave the int16 range (bounds: S1 8192, S2 3072,
+// S3 13108, S4 17000), so the C-typed stores are identities and are skipped.
+struct EdgeX {
+	bool on;        // this strip holds column 0 or column w-1
+	bool first;     // this lane holds column 0 (as its element 0)
+	bool last;      // this lane holds column w-1 ...
+	int kl;         // ... as its element kl
+};
+
+__device__ __forceinline__ EdgeX make_edge_x(int cb, int w, bool on)
 {
-	int nl, nr;
+	EdgeX e;
+	e.on = on;
+	e.first = cb == 0;
+	e.last = cb == ((w - 1) & ~7);
+	e.kl = (w - 1) & 7;
+	return e;
+}
+
+template <bool SH, int TRANS, bool NT = false>
+__device__ __forceinline__ void row_fwd(int (&v)[8], const EdgeX &e)
+{
+	constexpr bool S = SH && !NT;
+	int nl, nr, o[8];
 	// S1: even columns
 	nl = __shfl_up_sync(FULL, v[7], 1);
 #pragma unroll
-	for (int k = 0; k < 8; k += 2) {
-		int l = k ? v[k - 1] : nl, r = v[k + 1], c = cb + k;
-		int g = fS1<SH, TRANS>(v[k], l, r);
-		if (EDGE) {
-			if (c == 0) g = fS1_first<SH, TRANS>(v[k], r);
-			else if (c == w - 1) g = fS1_last<SH, TRANS>(v[k], l);
+	for (int k = 0; k < 8; k += 2) { o[k] = v[k]; v[k] = fS1<S, TRANS>(v[k], k ? v[k - 1] : nl, v[k + 1]); }
+	if (e.on) {
+		if (e.first) v[0] = fS1_first<S, TRANS>(o[0], v[1]);
+		if (e.last) {
+#pragma unroll
+			for (int k = 0; k < 8; k += 2) if (e.kl == k) v[k] = fS1_last<S, TRANS>(o[k], k ? v[k - 1] : nl);
 		}
-		v[k] = g;
 	}
 	// S2: odd columns
 	nr = __shfl_down_sync(FULL, v[0], 1);
 #pragma unroll
-	for (int k = 1; k < 8; k += 2) {
-		int l = v[k - 1], r = k < 7 ? v[k + 1] : nr, c = cb + k;
-		int g = fS2<SH, TRANS>(v[k], l, r);
-		if (EDGE && c == w - 1) g = fS2_last<SH, TRANS>(v[k], l);
-		v[k] = g;
+	for (int k = 1; k < 8; k += 2) { o[k] = v[k]; v[k] = fS2<S, TRANS>(v[k], v[k - 1], k < 7 ? v[k + 1] : nr); }
+	if (e.on && e.last) {
+#pragma unroll
+		for (int k = 1; k < 8; k += 2) if (e.kl == k) v[k] = fS2_last<S, TRANS>(o[k], v[k - 1]);
 	}
 	if (TRANS != T97) return;
 	// S3
 	nl = __shfl_up_sync(FULL, v[7], 1);
 #pragma unroll
-	for (int k = 0; k < 8; k += 2) {
-		int l = k ? v[k - 1] : nl, r = v[k + 1], c = cb + k;
-		int g = fS3<SH, TRANS>(v[k], l, r);
-		if (EDGE) {
-			if (c == 0) g = fS3_edge<SH, TRANS>(v[k], r);
-			else if (c == w - 1) g = fS3_edge<SH, TRANS>(v[k], l);
+	for (int k = 0; k < 8; k += 2) { o[k] = v[k]; v[k] = fS3<S, TRANS>(v[k], k ? v[k - 1] : nl, v[k + 1]); }
+	if (e.on) {
+		if (e.first) v[0] = fS3_edge<S, TRANS>(o[0], v[1]);
+		if (e.last) {
+#pragma unroll
+			for (int k = 0; k < 8; k += 2) if (e.kl == k) v[k] = fS3_edge<S, TRANS>(o[k], k ? v[k - 1] : nl);
 		}
-		v[k] = g;
 	}
 	// S4
 	nr = __shfl_down_sync(FULL, v[0], 1);
 #pragma unroll
-	for (int k = 1; k < 8; k += 2) {
-		int l = v[k - 1], r = k < 7 ? v[k + 1] : nr, c = cb + k;
-		int g = fS4<SH, TRANS>(v[k], l, r);
-		if (EDGE && c == w - 1) g = fS4_last<SH, TRANS>(v[k], l);
-		v[k] = g;
+	for (int k = 1; k < 8; k += 2) { o[k] = v[k]; v[k] = fS4<S, TRANS>(v[k], v[k - 1], k < 7 ? v[k + 1] : nr); }
+	if (e.on && e.last) {
+#pragma unroll
+		for (int k = 1; k < 8; k += 2) if (e.kl == k) v[k] = fS4_last<S, TRANS>(o[k], v[k - 1]);
 	}
 }
 
-template <bool SH, int TRANS, bool EDGE>
-__device__ __forceinline__ void row_inv(int (&v)[8], int cb, int w)
+template <bool SH, int TRANS>
+__device__ __forceinline__ void row_inv(int (&v)[8], const EdgeX &e)
 {
-	int nl, nr;
+	int nl, nr, o[8];
 	if (TRANS == T97) {
 		// U4: odd columns
 		nr = __shfl_down_sync(FULL, v[0], 1);
 #pragma unroll
-		for (int k = 1; k < 8; k += 2) {
-			int l = v[k - 1], r = k < 7 ? v[k + 1] : nr, c = cb + k;
-			int g = iU4<SH, TRANS>(v[k], l, r);
-			if (EDGE && c == w - 1) g = iU4_last<SH, TRANS>(v[k], l);
-			v[k] = g;
+		for (int k = 1; k < 8; k += 2) { o[k] = v[k]; v[k] = iU4<SH, TRANS>(v[k], v[k - 1], k < 7 ? v[k + 1] : nr); }
+		if (e.on && e.last) {
+#pragma unroll
+			for (int k = 1; k < 8; k += 2) if (e.kl == k) v[k] = iU4_last<SH, TRANS>(o[k], v[k - 1]);
 		}
 		// U3: even columns
 		nl = __shfl_up_sync(FULL, v[7], 1);
 #pragma unroll
-		for (int k = 0; k < 8; k += 2) {
-			int l = k ? v[k - 1] : nl, r = v[k + 1], c = cb + k;
-			int g = iU3<SH, TRANS>(v[k], l, r);
-			if (EDGE) {
-				if (c == 0) g = iU3_edge<SH, TRANS>(v[k], r);
-				else if (c == w - 1) g = iU3_edge<SH, TRANS>(v[k], l);
+		for (int k = 0; k < 8; k += 2) { o[k] = v[k]; v[k] = iU3<SH, TRANS>(v[k], k ? v[k - 1] : nl, v[k + 1]); }
+		if (e.on) {
+			if (e.first) v[0] = iU3_edge<SH, TRANS>(o[0], v[1]);
+			if (e.last) {
+#pragma unroll
+				for (int k = 0; k < 8; k += 2) if (e.kl == k) v[k] = iU3_edge<SH, TRANS>(o[k], k ? v[k - 1] : nl);
 			}
-			v[k] = g;
 		}
 	}
 	// U2: odd columns
 	nr = __shfl_down_sync(FULL, v[0], 1);
 #pragma unroll
-	for (int k = 1; k < 8; k += 2) {
-		int l = v[k - 1], r = k < 7 ? v[k + 1] : nr, c = cb + k;
-		int g = iU2<SH, TRANS>(v[k], l, r);
-		if (EDGE && c == w - 1) g = iU2_last<SH, TRANS>(v[k], l);
-		v[k] = g;
+	for (int k = 1; k < 8; k += 2) { o[k] = v[k]; v[k] = iU2<SH, TRANS>(v[k], v[k - 1], k < 7 ? v[k + 1] : nr); }
+	if (e.on && e.last) {
+#pragma unroll
+		for (int k = 1; k < 8; k += 2) if (e.kl == k) v[k] = iU2_last<SH, TRANS>(o[k], v[k - 1]);
 	}
 	// U1: even columns
 	nl = __shfl_up_sync(FULL, v[7], 1);
 #pragma unroll
-	for (int k = 0; k < 8; k += 2) {
-		int l = k ? v[k - 1] : nl, r = v[k + 1], c = cb + k;
-		int g = iU1<SH, TRANS>(v[k], l, r);
-		if (EDGE) {
-			if (c == 0) g = iU1_first<SH, TRANS>(v[k], r);
-			else if (c == w - 1) g = iU1_last<SH, TRANS>(v[k], l);
+	for (int k = 0; k < 8; k += 2) { o[k] = v[k]; v[k] = iU1<SH, TRANS>(v[k], k ? v[k - 1] : nl, v[k + 1]); }
+	if (e.on) {
+		if (e.first) v[0] = iU1_first<SH, TRANS>(o[0], v[1]);
+		if (e.last) {
+#pragma unroll
+			for (int k = 0; k < 8; k += 2) if (e.kl == k) v[k] = iU1_last<SH, TRANS>(o[k], k ? v[k - 1] : nl);
 		}
-		v[k] = g;
 	}
 }
 
@@ -236,16 +251,13 @@ RIC_VSTEP(vU1, (iU1<SH, TRANS>(x[k], l[k], r[k])), (iU1_first<SH, TRANS>(x[k], r
 struct QuantBand {
 	int Q, iQ, T, Te;  // T = Q>>1 (full blocks), Te = (Q+((Q-(Q>>2))>>1))>>1 (partial blocks)
 	int thr[16];
+	int fast;          // 1 <= Q <= 16383: every candidate / threshold is a non-negative int16, so signed and
+	                   // unsigned views agree and the rank thresholds can be compared in the key domain
+	int kthr[32];      // fast: thr[n] << 4 (n < 16), INT_MAX beyond
 };
 
 template <bool SH>
 __device__ __forceinline__ unsigned uview(int v) { return SH ? (unsigned)(v & 0xFFFF) : (unsigned)v; }
-
-__device__ __forceinline__ int fold_s2u(int c)  // s2u_, utils.h:95-99
-{
-	int m = c >> 31;
-	return (2 * c + m) ^ (m * 2);
-}
 
 // Batcher odd-even merge sort of 16 keys, descending: 63 compare-exchanges written out so that the
 // keys provably stay in registers (a rolled network would index them dynamically -> local memory).
@@ -268,70 +280,73 @@ __device__ __forceinline__ void sort16_desc(int (&s)[16])
 // the number of non-zero outputs.  bw/bh: valid columns/rows (4,4 = full block -> rank-threshold
 // path; otherwise the plain dead-zone path of the partial-block overload).  qb points to shared
 // memory.  The candidate ranking reproduces the reference's stable insertion sort (descending
-// unsigned value, ties in raster order) through distinct keys (value<<4 | 15-pos).
+// unsigned value, ties in raster order) through distinct keys (value<<4 | 15-pos):
+//   survivors = the m* largest candidates, m* = 1 + max{i : f_(i) >= thr[cnt+i]}  (bandcodec.cpp:188-199).
 template <bool SH>
 __device__ __forceinline__ int quant_block(int (&c)[16], const QuantBand *qb, int bw, int bh)
 {
-	const int Q_iQ = qb->iQ;
-	int cnt = 0;
-	if (bw == 4 && bh == 4) {
-		const int T = qb->T, thr0 = qb->thr[0];
-		const unsigned uthr0 = uview<SH>(thr0);
-		int key[16];
-		int nc = 0;
+	const bool full = bw == 4 && bh == 4;
+	const int T = full ? qb->T : qb->Te;
+	const unsigned T2 = (unsigned)(2 * T);
+	if (!full) {
 #pragma unroll
-		for (int k = 0; k < 16; k++) {
-			int v = c[k];
-			key[k] = 0;
-			if ((unsigned)(v + T) <= (unsigned)(2 * T)) { c[k] = 0; continue; }
-			int f = TR<SH>(fold_s2u(v));
-			unsigned uf = uview<SH>(f);
-			if (uf < uthr0) {
-				key[k] = (int)(uf << 4) | (15 - k);
-				c[k] = f;
-				nc++;
-			} else {
-				cnt++;
-				int a = (int)(uf >> 1);
-				int q = (a * Q_iQ + (1 << 15)) >> 16;
-				c[k] = TR<SH>((q << 1) | (f & 1));
+		for (int k = 0; k < 16; k++)
+			if ((k & 3) >= bw || (k >> 2) >= bh) c[k] = 0;  // outside the band: treated as dead
+	}
+	// pass 1: dead zone only.  Warps whose blocks are all dead (chroma, coarse quantisers) stop here.
+	unsigned alive = 0;
+#pragma unroll
+	for (int k = 0; k < 16; k++) alive |= ((unsigned)(c[k] + T) > T2) ? (1u << k) : 0u;
+	if (!__any_sync(__activemask(), alive != 0)) {
+#pragma unroll
+		for (int k = 0; k < 16; k++) c[k] = 0;
+		return 0;
+	}
+	// pass 2 (branch-free): fold, split into sure non-zeros (quantised now) and rank candidates
+	const int iQ = qb->iQ;
+	const unsigned uthr0 = full ? uview<SH>(qb->thr[0]) : 0u;  // partial blocks have no candidates
+	int key[16];
+	int cnt = 0, nc = 0;
+#pragma unroll
+	for (int k = 0; k < 16; k++) {
+		const int v = c[k];
+		const bool live = (alive >> k) & 1;
+		const int sgn = (int)((unsigned)v >> 31);
+		const unsigned uf = uview<SH>(2 * abs(v) + sgn);        // s2u_ (utils.h:95-99), C-typed
+		const bool cand = live && uf < uthr0;
+		const int qq = ((int)(uf >> 1) * iQ + (1 << 15)) >> 16;  // int arithmetic as in the reference (:172)
+		c[k] = !live ? 0 : cand ? (2 | sgn) : ((qq << 1) | sgn);
+		key[k] = cand ? (int)(uf << 4 | (unsigned)(15 - k)) : 0;
+		cnt += (live && !cand) ? 1 : 0;
+		nc += cand ? 1 : 0;
+	}
+	if (__any_sync(__activemask(), nc > 0)) {
+		int s[16];
+#pragma unroll
+		for (int k = 0; k < 16; k++) s[k] = key[k];
+		sort16_desc(s);
+		int kstar = 0x7fffffff, m = 0;
+		if (qb->fast) {
+			const int *kt = qb->kthr + cnt;
+#pragma unroll
+			for (int i = 0; i < 16; i++) {
+				const bool pass = s[i] >= kt[i];  // non-candidates (key 0) never pass: kthr > 0 whenever candidates exist
+				kstar = pass ? s[i] : kstar;
+				m = pass ? i + 1 : m;
 			}
-		}
-		if (__any_sync(__activemask(), nc > 0)) {
-			int s[16];
-#pragma unroll
-			for (int k = 0; k < 16; k++) s[k] = key[k];
-			sort16_desc(s);
-			int kstar = 0x7fffffff;
+		} else {
 #pragma unroll
 			for (int i = 0; i < 16; i++) {
 				if (s[i] != 0) {
-					int fs = TR<SH>(s[i] >> 4);
-					if (!(fs < qb->thr[(cnt + i) & 15])) kstar = s[i];
-				}
-			}
-#pragma unroll
-			for (int k = 0; k < 16; k++) {
-				if (key[k] != 0) {
-					if (key[k] >= kstar) { c[k] = 2 | (c[k] & 1); cnt++; }
-					else c[k] = 0;
+					const int fs = TR<SH>(s[i] >> 4);  // signed C compare, :191
+					if (!(fs < qb->thr[(cnt + i) & 15])) { kstar = s[i]; m = i + 1; }
 				}
 			}
 		}
-	} else {
-		const int T = qb->Te;
 #pragma unroll
-		for (int k = 0; k < 16; k++) {
-			if ((k & 3) >= bw || (k >> 2) >= bh) continue;
-			int v = c[k];
-			if ((unsigned)(v + T) <= (unsigned)(2 * T)) { c[k] = 0; continue; }
-			int f = TR<SH>(fold_s2u(v));
-			unsigned uf = uview<SH>(f);
-			cnt++;
-			int a = (int)(uf >> 1);
-			int q = (a * Q_iQ + (1 << 15)) >> 16;
-			c[k] = TR<SH>((q << 1) | (f & 1));
-		}
+		for (int k = 0; k < 16; k++)
+			c[k] = ((unsigned)(key[k] - 1) < (unsigned)(kstar - 1)) ? 0 : c[k];  // candidate ranked below the last survivor
+		cnt += m;
 	}
 	return cnt;
 }

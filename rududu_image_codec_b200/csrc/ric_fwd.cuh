@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 	const int cb = x0 - LANE_W + lane * LANE_W;       // first column of this lane
 	const bool col_ok = cb >= 0 && cb < w;            // lane has at least one real column
 	const bool lane_out = lane >= 1 && lane <= 30;    // lane owns output columns
-	const bool edge_x = (x0 == 0) || (w <= x0 + STRIP_W + LANE_W);
+	const EdgeX ex = make_edge_x(cb, w, (x0 == 0) || (w <= x0 + STRIP_W + LANE_W));
+	constexpr bool NT = SRC == SRC_U8_GRAY || SRC == SRC_U8_RGB;  // rows straight from 8-bit pixels cannot wrap
 	const int y0 = sy * P.seg_rows;
 	const int y1 = min(h, y0 + P.seg_rows);
 	const int y1r = (y1 + 7) & ~7;
@@ -314,8 +315,8 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 			load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
 			load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 		}
-		if (edge_x) { row_fwd<SH, TRANS, true>(ne, cb, w); row_fwd<SH, TRANS, true>(no, cb, w); }
-		else { row_fwd<SH, TRANS, false>(ne, cb, w); row_fwd<SH, TRANS, false>(no, cb, w); }
+		row_fwd<SH, TRANS, NT>(ne, ex);
+		row_fwd<SH, TRANS, NT>(no, ex);
 
 		const int r1 = 2 * t, r2 = 2 * t - 1, r3 = 2 * t - 2, r4 = 2 * t - 3;
 		// rows r4-1 .. r1+1 are touched; edge formulas if that range meets row 0 or row h-1

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 	const int cb = x0 - LANE_W + lane * LANE_W;
 	const bool col_ok = cb >= 0 && cb < w;
 	const bool lane_out = lane >= 1 && lane <= 30 && cb < w;
-	const bool edge_x = (x0 == 0) || (w <= x0 + STRIP_W + LANE_W);
+	const EdgeX ex = make_edge_x(cb, w, (x0 == 0) || (w <= x0 + STRIP_W + LANE_W));
 	const int y0 = sy * P.seg_rows;
 	const int y1 = min(h, y0 + P.seg_rows);
 	const int bc = cb >> 1;  // band column of this lane's first even/odd sample
@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 		int oe[8], oo[8];
 #pragma unroll
 		for (int k = 0; k < 8; k++) { oe[k] = se3[k]; oo[k] = so4[k]; }
-		if (edge_x) { row_inv<SH, TRANS, true>(oe, cb, w); row_inv<SH, TRANS, true>(oo, cb, w); }
-		else { row_inv<SH, TRANS, false>(oe, cb, w); row_inv<SH, TRANS, false>(oo, cb, w); }
+		row_inv<SH, TRANS>(oe, ex);
+		row_inv<SH, TRANS>(oo, ex);
 		// rotate
 #pragma unroll
 		for (int k = 0; k < 8; k++) { so2[k] = so4[k]; se3[k] = se0[k]; se0[k] = xe[k]; so4[k] = xo[k]; }

@@ -1,0 +1,52 @@
+"""The C++ class shim (include/rududu_b200/wavelet2d.h), driven the way ric.cpp drives the reference."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oraclebind
+from rududu_image_codec_b200.synth import synth_image
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+PKG = os.path.join(ROOT, "rududu_image_codec_b200")
+
+
+def _build(tmp_path):
+    exe = str(tmp_path / "shim_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-L" + PKG, "-lrududu_b200",
+                           "-Wl,-rpath," + PKG])
+    return exe
+
+
+def test_shim_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+    exe = _build(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    r = subprocess.run([exe, "64", "64", "5", "96", "36", "/dev/null", "a", "b", "c"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(512, 512), (517, 389)])
+def test_shim_matches_oracle(tmp_path, w, h):
+    exe = _build(tmp_path)
+    q = 9
+    plane = oraclebind.colour_fwd(synth_image(0, w, h, 1), q)[0]
+    Quant, lam = oraclebind.plane_quant(q, 1, 0)
+    o = oraclebind.Oracle(w, h, 5)
+    want = o.forward(plane)
+    o.quant(want, Quant, lam)
+    signed = want.copy()
+    o.unfold(signed)
+    plane.tofile(tmp_path / "plane.s16")
+    signed.tofile(tmp_path / "signed.bin")
+    r = subprocess.run([exe, str(w), str(h), "5", str(Quant), str(lam), str(tmp_path / "plane.s16"),
+                        str(tmp_path / "arena.bin"), str(tmp_path / "signed.bin"), str(tmp_path / "out.s16")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(tmp_path / "arena.bin", dtype=np.uint8), want)
+    o.tsuqi(signed, Quant)
+    assert np.array_equal(np.fromfile(tmp_path / "out.s16", dtype=np.int16).reshape(h, w), o.inverse(signed))
