@@ -57,3 +57,24 @@ def ref_decode_arenas(o, arenas, ch, q, trans=0):
         planes[p] = r.transform_inv()
         r.close()
     return oraclebind.colour_inv(planes, q)
+
+
+def ref_payload_from_arenas(o, arenas, ch, trans=0):
+    """Run the reference's ENTROPY half of CodeBand (wavelet2d.cpp:119-159 minus the quantiser calls,
+    oracle/ref_harness.cpp:entropy_half) over already-quantised band arenas, planes in ric's order
+    (Y, Cg, Co -- ric.cpp:163-168), and return the payload exactly as ric writes it after the header."""
+    import ctypes as C
+    L = refbind.lib()
+    buf = np.zeros(o.w * o.h * ch * 2 + 4096, dtype=np.uint8)
+    codec = L.ref_codec_new_enc(buf.ctypes.data)
+    order = [2, 1, 0] if ch == 3 else [0]
+    for p in order:
+        r = refbind.RefWavelet(o.w, o.h, o.g.levels, o.g.level_chg, trans)
+        a = arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes]
+        for i in range(o.nbands):
+            r.set_band(i, o.band_view(a, i))
+        L.ref_entropy_encode(r.h, codec)
+        r.close()
+    n = L.ref_codec_end(codec, buf.ctypes.data)
+    L.ref_codec_free(codec)
+    return buf[2:n].copy()

@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import oraclebind
-from refutil import crc
+import refbind
+from refutil import crc, ref_payload_from_arenas
 from rududu_image_codec_b200 import capi
 from rududu_image_codec_b200.synth import synth_image
 
@@ -187,3 +188,20 @@ def test_error_codes():
         with pytest.raises(capi.RicError):
             c.encode_u8(np.zeros((1, 1, 64, 64), np.uint8), 40)
     assert L.ric_last_error()
+
+
+@pytest.mark.skipif(not refbind.available(), reason="oracle/_ref/libric_ref.so not built")
+def test_ric_bitstream_bytes_from_gpu_bands(golden):
+    """.ric payload parity: GPU-produced band arenas handed to the reference's own entropy coder
+    (CBandCodec::pred/tree + CMuxCodec, unmodified) give the reference's bitstream byte for byte
+    (SURVEY.md Appendix C payload size + CRC32), for every golden shape that is cheap to code on the CPU."""
+    for k in golden["kats"]:
+        w, h, ch, q = k["w"], k["h"], k["ch"], k["q"]
+        if w * h * ch > 3840 * 2160 * 3 or k["trans"] != 0 or (w * h * ch > 1 << 22 and q not in (9, 27)):
+            continue
+        img = synth_image(k["idx"], w, h, ch)
+        o = oraclebind.Oracle(w, h, k["levels"], trans=k["trans"])
+        with capi.Context(w, h, ch, k["levels"], trans=k["trans"]) as c:
+            arenas = c.encode_u8(img[None], q)
+        payload = ref_payload_from_arenas(o, arenas, ch, k["trans"])
+        assert (len(payload), crc(payload)) == (k["payload_bytes"], k["payload_crc"]), k

@@ -9,7 +9,7 @@ import pytest
 
 import oraclebind
 import refbind
-from refutil import crc, ref_decode_arenas, ref_encode_arenas, ref_plane_arena
+from refutil import crc, ref_decode_arenas, ref_encode_arenas, ref_payload_from_arenas, ref_plane_arena
 from rududu_image_codec_b200.synth import synth_image
 
 pytestmark = pytest.mark.skipif(not refbind.available(), reason="oracle/_ref/libric_ref.so not built")
@@ -153,3 +153,16 @@ def test_kat_small(golden):
         assert (len(p), crc(p)) == (k["payload_bytes"], k["payload_crc"])
         d = refbind.decompress(p, k["w"], k["h"], k["ch"], k["q"], k["trans"], k["levels"])
         assert crc(d) == k["dec8_crc"]
+
+
+@pytest.mark.parametrize("w,h,ch,q", [(512, 512, 1, 9), (320, 200, 3, 9), (246, 131, 3, 4), (512, 384, 3, 27)])
+def test_quant_half_plus_entropy_half_is_codeband(w, h, ch, q):
+    """The split INTEGRATION.md relies on: quantiser half (GPU-able) then entropy half (host) gives
+    the byte-identical payload of the reference's monolithic CodeBand -- also when the quantised
+    arenas come from our restatement instead of the reference's buildTree."""
+    img = synth_image(5, w, h, ch)
+    want = refbind.compress(img, q)
+    o, arenas = ref_encode_arenas(img, q)
+    assert np.array_equal(ref_payload_from_arenas(o, arenas, ch), want)
+    ours = oraclebind.Oracle(w, h, 5).encode_image(img, q)
+    assert np.array_equal(ref_payload_from_arenas(o, ours, ch), want)
