@@ -59,19 +59,28 @@ __device__ __forceinline__ int fS2(int x, int l, int r)
 template <bool SH, int TRANS>
 __device__ __forceinline__ int fS2_last(int x, int l) { return TRANS == T97 ? TR<SH>(x - (l >> 3)) : TR<SH>(x + (l >> 1)); }
 
+// S3 / S4 (and U2 / U1 below) results are only ever consumed through a truncating use -- the
+// (C)(l + r) temporary of the next step, a 16-bit store, or an edge formula that truncates its
+// operand itself -- so their own C-typed store is deferred (the low 16 bits are always right:
+// + - * are ring homomorphisms mod 2^16).  Everything that feeds a shift stays truncated.
 template <bool SH, int TRANS>
-__device__ __forceinline__ int fS3(int x, int l, int r) { return TRANS == T97 ? TR<SH>(x + m08i(l + r)) : x; }
+__device__ __forceinline__ int fS3(int x, int l, int r) { return TRANS == T97 ? x + m08i(l + r) : x; }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int fS3_edge(int x, int n) { return TRANS == T97 ? TR<SH>(x + 2 * m08c<SH>(n)) : x; }
 
 template <bool SH, int TRANS>
 __device__ __forceinline__ int fS4(int x, int l, int r)
 {
-	if (TRANS == T97) { int t = TR<SH>(l + r); return TR<SH>(x + ((t >> 1) - (t >> 5))); }
+	if (TRANS == T97) { int t = TR<SH>(l + r); return x + ((t >> 1) - (t >> 5)); }
 	return x;
 }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int fS4_last(int x, int l) { return TRANS == T97 ? TR<SH>(x + (l - (l >> 4))) : x; }
+__device__ __forceinline__ int fS4_last(int x, int l)
+{
+	if (TRANS != T97) return x;
+	l = TR<SH>(l);  // S3 results arrive un-truncated
+	return TR<SH>(x + (l - (l >> 4)));
+}
 
 // ---- inverse lifting steps (Appendix A.2 / A.3): U4 undoes S4, ... U1 undoes S1.
 template <bool SH, int TRANS>
@@ -81,7 +90,12 @@ __device__ __forceinline__ int iU4(int x, int l, int r)
 	return x;
 }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int iU4_last(int x, int l) { return TRANS == T97 ? TR<SH>(x - (l - (l >> 4))) : x; }
+__device__ __forceinline__ int iU4_last(int x, int l)
+{
+	if (TRANS != T97) return x;
+	l = TR<SH>(l);  // row pass: vertical U1 results arrive un-truncated
+	return TR<SH>(x - (l - (l >> 4)));
+}
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU3(int x, int l, int r) { return TRANS == T97 ? TR<SH>(x - m08i(l + r)) : x; }
 template <bool SH, int TRANS>
@@ -89,15 +103,15 @@ __device__ __forceinline__ int iU3_edge(int x, int n) { return TRANS == T97 ? TR
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU2(int x, int l, int r)
 {
-	if (TRANS == T97) return TR<SH>(x + ((l + r) >> 4));
-	return TR<SH>(x - ((l + r) >> 2));
+	if (TRANS == T97) return x + ((l + r) >> 4);
+	return TR<SH>(x - ((l + r) >> 2));  // 5/3: feeds the un-truncated (l + r) >> 1 of U1
 }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU2_last(int x, int l) { return TRANS == T97 ? TR<SH>(x + (l >> 3)) : TR<SH>(x - (l >> 1)); }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU1(int x, int l, int r)
 {
-	if (TRANS == T97) { int t = TR<SH>(l + r); return TR<SH>(x + (t + (t >> 1))); }
+	if (TRANS == T97) { int t = TR<SH>(l + r); return x + (t + (t >> 1)); }
 	return TR<SH>(x + ((l + r) >> 1));
 }
 template <bool SH, int TRANS>

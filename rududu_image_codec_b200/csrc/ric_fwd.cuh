@@ -298,25 +298,33 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 	for (int k = 0; k < 8; k++) so1[k] = se1[k] = so2[k] = se3[k] = 0;
 
 	const int t_begin = (y0 >> 1) - 2, t_last = (y1r >> 1) + 1;
-	RawRow<SRC> rawE, rawO;
+	RawRow<SRC> raw;
 	{
-		int re = 2 * t_begin, ro = re + 1;
-		load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
-		load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
+		const int r0 = 2 * t_begin;
+		load_raw<SRC>(raw, src, (long long)r0 * P.src_pitch, cb, col_ok && r0 >= 0 && r0 < h, P.src_plane_stride, plane);
 	}
+	int ne[8];
+#pragma unroll
+	for (int k = 0; k < 8; k++) ne[k] = 0;
 
+	// One source row per iteration (conversion + horizontal lifting share one copy of the code for
+	// even and odd rows: the loop body must stay inside the instruction cache); the vertical
+	// pipeline advances on every odd row.
 #pragma unroll 1
-	for (int t = t_begin; t <= t_last; t++) {
-		int ne[8], no[8];
-		convert_raw<SRC>(rawE, ne, plane, P.shift);
-		convert_raw<SRC>(rawO, no, plane, P.shift);
-		{  // prefetch the next row pair
-			int re = 2 * t + 2, ro = re + 1;
-			load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
-			load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
+	for (int r = 2 * t_begin; r <= 2 * t_last + 1; r++) {
+		int no[8];
+		convert_raw<SRC>(raw, no, plane, P.shift);
+		{  // prefetch the next row
+			const int rn = r + 1;
+			load_raw<SRC>(raw, src, (long long)rn * P.src_pitch, cb, col_ok && rn >= 0 && rn < h, P.src_plane_stride, plane);
 		}
-		row_fwd<SH, TRANS, NT>(ne, ex);
 		row_fwd<SH, TRANS, NT>(no, ex);
+		if (!(r & 1)) {
+#pragma unroll
+			for (int k = 0; k < 8; k++) ne[k] = no[k];
+			continue;
+		}
+		const int t = r >> 1;
 
 		const int r1 = 2 * t, r2 = 2 * t - 1, r3 = 2 * t - 2, r4 = 2 * t - 3;
 		// rows r4-1 .. r1+1 are touched; edge formulas if that range meets row 0 or row h-1
@@ -343,6 +351,7 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 			if (P.ll_to_band) {
 				if (P.quant) {  // CBand::TSUQ(Quant, 0.5), wavelet2d.cpp:121,124
 					const int T = P.llT[cls], iQ = P.lliQ[cls];
+					l0 = TR<SH>(l0); l1 = TR<SH>(l1); l2 = TR<SH>(l2); l3 = TR<SH>(l3);  // S4 results arrive un-truncated
 					l0 = tsuq1<SH>(l0, T, iQ); l1 = tsuq1<SH>(l1, T, iQ); l2 = tsuq1<SH>(l2, T, iQ); l3 = tsuq1<SH>(l3, T, iQ);
 				}
 				if (lx + 4 <= ll_dimx) store4<SH>(rowp, lx, l0, l1, l2, l3);

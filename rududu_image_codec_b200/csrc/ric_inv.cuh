@@ -193,22 +193,22 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 			vU2<SH, TRANS, false>(so4, se3, se0, false, false);
 			vU1<SH, TRANS, false>(se3, so2, so4, false, false);
 		}
-		// finished: even row r1 (se3), odd row r2 (so4)
-		int oe[8], oo[8];
+		// finished: even row r1 (se3), odd row r2 (so4); both rows' horizontal passes are unrolled so
+		// that their dependency chains interleave (this kernel fits the instruction cache either way)
+		const int slot = RGB ? (t - t_begin) % 3 : 0;
 #pragma unroll
-		for (int k = 0; k < 8; k++) { oe[k] = se3[k]; oo[k] = so4[k]; }
-		row_inv<SH, TRANS>(oe, ex);
-		row_inv<SH, TRANS>(oo, ex);
-		// rotate
+		for (int half = 0; half < 2; half++) {
+			int o[8];
 #pragma unroll
-		for (int k = 0; k < 8; k++) { so2[k] = so4[k]; se3[k] = se0[k]; se0[k] = xe[k]; so4[k] = xo[k]; }
-
-		if (DST == DST_PLANE) {
-#pragma unroll
-			for (int half = 0; half < 2; half++) {
-				const int row = half ? r2 : r1;
-				const int *o = half ? oo : oe;
-				if (!(row >= y0 && row < y1 && lane_out)) continue;
+			for (int k = 0; k < 8; k++) o[k] = half ? so4[k] : se3[k];
+			row_inv<SH, TRANS>(o, ex);
+			const int row = half ? r2 : r1;
+			if (DST == DST_U8_RGB) {
+				s_stage[grp][slot][plane][half][lane] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+				continue;
+			}
+			if (!(row >= y0 && row < y1 && lane_out)) continue;
+			if (DST == DST_PLANE) {
 				if (SH) {
 					short *dp = (short *)P.dst + img * P.dst_img_stride + plane * P.dst_plane_stride + (long long)row * P.dst_pitch + cb;
 					*(uint4 *)dp = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
@@ -217,17 +217,11 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 					*(int4 *)dp = make_int4(o[0], o[1], o[2], o[3]);
 					*(int4 *)(dp + 4) = make_int4(o[4], o[5], o[6], o[7]);
 				}
-			}
-		} else if (DST == DST_U8_GRAY) {
-#pragma unroll
-			for (int half = 0; half < 2; half++) {
-				const int row = half ? r2 : r1;
-				const int *o = half ? oo : oe;
-				if (!(row >= y0 && row < y1 && lane_out)) continue;
+			} else {  // DST_U8_GRAY
 				unsigned b[8];
 #pragma unroll
 				for (int k = 0; k < 8; k++) {  // ric.cpp:229 / :237-240
-					int v = o[k];
+					int v = TR<SH>(o[k]);  // the last lifting step leaves its result un-truncated
 					v = P.shift ? clip255((int)(short)(128 + ((v + 8) >> 4))) : (v + 128);
 					b[k] = (unsigned)v & 0xFF;
 				}
@@ -235,12 +229,14 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 				                    (long long)row * P.dst_pitch + cb;
 				*(uint2 *)dp = make_uint2(pack4b(b[0], b[1], b[2], b[3]), pack4b(b[4], b[5], b[6], b[7]));
 			}
-		} else {
+		}
+		// rotate
+#pragma unroll
+		for (int k = 0; k < 8; k++) { so2[k] = so4[k]; se3[k] = se0[k]; se0[k] = xe[k]; so4[k] = xo[k]; }
+
+		if (DST == DST_U8_RGB) {
 			// stage this plane's two rows; every third iteration (and at the end) the three warps of the
 			// group swap planes through shared memory and each converts one iteration's pixel rows
-			const int slot = (t - t_begin) % 3;
-			s_stage[grp][slot][plane][0][lane] = make_uint4(pack2(oe[0], oe[1]), pack2(oe[2], oe[3]), pack2(oe[4], oe[5]), pack2(oe[6], oe[7]));
-			s_stage[grp][slot][plane][1][lane] = make_uint4(pack2(oo[0], oo[1]), pack2(oo[2], oo[3]), pack2(oo[4], oo[5]), pack2(oo[6], oo[7]));
 			if (slot == 2 || t == t_last) {
 				asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory");
 				const int my = plane;  // this warp converts the rows staged in slot `plane`
