@@ -36,6 +36,8 @@ struct ric_ctx {
 	int device, max_batch;
 	int sm_count;
 	cudaStream_t stream;
+	cudaStream_t pipe[3];    // host-buffer calls: chunks of the batch alternate over these (copy/compute overlap)
+	int img0;                // first image slot used by the launch functions (chunked pipelining)
 	// device buffers
 	unsigned char *d_src;   // [max_batch][channels][height][src_pitch] u8
 	size_t src_pitch;
@@ -229,6 +231,8 @@ int ric_destroy(ric_ctx *c)
 			if (c->ev[d][i]) cudaEventDestroy(c->ev[d][i]);
 	for (int i = 0; i < RIC_MAX_LEVELS; i++) cudaFree(c->d_ll[i]);
 	if (c->stream) cudaStreamDestroy(c->stream);
+	for (int i = 0; i < 3; i++)
+		if (c->pipe[i]) cudaStreamDestroy(c->pipe[i]);
 	delete c;
 	return RIC_OK;
 }
@@ -268,6 +272,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 		}                                                                            \
 	} while (0)
 	CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 3; i++) CKD(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
 	const size_t nb = (size_t)max_batch, ch = (size_t)channels;
 	c->src_pitch = ((size_t)width + 7 + 8) & ~(size_t)7;  // >= roundup8(w), one spare vector
 	CKD(cudaMalloc(&c->d_src, nb * ch * height * c->src_pitch + 64));
@@ -371,25 +376,25 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 			P.src = d_src; src = src_kind;
 			P.src_img_stride = src_img_stride; P.src_plane_stride = src_plane_stride; P.src_pitch = src_pitch;
 		} else {
-			P.src = c->d_ll[lv - 1];
 			src = c->ll_es[lv - 1] == 4 && g.lev_int[lv - 1] ? SRC_S32 : SRC_S16;
 			P.src_pitch = c->ll_pitch[lv - 1];
 			P.src_plane_stride = (long long)g.lev_h[lv] * P.src_pitch;
 			P.src_img_stride = P.src_plane_stride * g.channels;
+			P.src = (const char *)c->d_ll[lv - 1] + (size_t)c->img0 * P.src_img_stride * (src == SRC_S32 ? 4 : 2);
 		}
 		P.ll_to_band = last;
 		if (!last) {
-			P.ll = c->d_ll[lv];
 			P.ll_pitch = c->ll_pitch[lv];
 			P.ll_plane_stride = (long long)g.lev_h[lv + 1] * P.ll_pitch;
 			P.ll_img_stride = P.ll_plane_stride * g.channels;
+			P.ll = (char *)c->d_ll[lv] + (size_t)c->img0 * P.ll_img_stride * (g.lev_int[lv] ? 4 : 2);
 		}
 		P.arena = d_arena;
 		P.arena_plane_stride = (long long)g.arena_bytes;
 		P.arena_img_stride = (long long)g.arena_bytes * g.channels;
-		P.flags = c->d_flags;
 		P.flags_plane_stride = (long long)g.flag_bytes;
 		P.flags_img_stride = (long long)g.flag_bytes * g.channels;
+		P.flags = c->d_flags + (size_t)c->img0 * P.flags_img_stride;
 		for (int o = 0; o < 3; o++) {
 			P.band[o] = band_ref(g, 3 * lv + o);
 			if (lv > 0) P.child[o] = band_ref(g, 3 * (lv - 1) + o);
@@ -448,20 +453,20 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		if (coarsest) P.llsrc = LLSRC_BAND;
 		else {
 			P.llsrc = g.lev_int[lv + 1] ? LLSRC_S32 : LLSRC_S16;
-			P.ll = c->d_ll[lv];
 			P.ll_pitch = c->ll_pitch[lv];
 			P.ll_plane_stride = (long long)g.lev_h[lv + 1] * P.ll_pitch;
 			P.ll_img_stride = P.ll_plane_stride * g.channels;
+			P.ll = (const char *)c->d_ll[lv] + (size_t)c->img0 * P.ll_img_stride * (g.lev_int[lv + 1] ? 4 : 2);
 		}
 		if (lv == 0) {
 			dst = dst_kind;
 			P.dst = d_dst; P.dst_img_stride = dst_img_stride; P.dst_plane_stride = dst_plane_stride; P.dst_pitch = dst_pitch;
 		} else {
 			dst = DST_PLANE;
-			P.dst = c->d_ll[lv - 1];
 			P.dst_pitch = c->ll_pitch[lv - 1];
 			P.dst_plane_stride = (long long)g.lev_h[lv] * P.dst_pitch;
 			P.dst_img_stride = P.dst_plane_stride * g.channels;
+			P.dst = (char *)c->d_ll[lv - 1] + (size_t)c->img0 * P.dst_img_stride * (g.lev_int[lv] ? 4 : 2);
 		}
 		for (int o = 0; o < 3; o++) P.band[o] = band_ref(g, 3 * lv + o);
 		P.lband = band_ref(g, 3 * g.nlev);
@@ -546,6 +551,17 @@ int ric_decode_u8_device(ric_ctx *c, const void *d_arenas, int n, int q, uint8_t
 	                      (cudaStream_t)stream);
 }
 
+// Host-buffer entry points: the batch is cut into chunks that alternate over three streams, so the
+// H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap (each chunk
+// owns its image slots of every device buffer, LL scratch and flags included).
+static int chunk_images(int n) { return n >= 12 ? (n + 7) / 8 : n >= 4 ? 2 : 1; }
+
+static int sync_pipe(ric_ctx *c)
+{
+	for (int i = 0; i < 3; i++) CK(cudaStreamSynchronize(c->pipe[i]));
+	return RIC_OK;
+}
+
 int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
 {
 	int rc = check_batch(c, n, q, "ric_encode_u8");
@@ -553,13 +569,24 @@ int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
 	if (!src || !arenas) return set_err(RIC_E_ARG, "ric_encode_u8: null buffer");
 	const HostGeom &g = c->g;
 	CK(cudaSetDevice(c->device));
-	const size_t rows = (size_t)n * g.channels * g.height;
-	CK(cudaMemcpy2DAsync(c->d_src, c->src_pitch, src, g.width, g.width, rows, cudaMemcpyHostToDevice, c->stream));
-	rc = ric_encode_u8_device(c, c->d_src, c->src_pitch, n, q, c->d_arena, c->stream);
-	if (rc) return rc;
-	CK(cudaMemcpyAsync(arenas, c->d_arena, (size_t)n * g.channels * g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
-	return RIC_OK;
+	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	const int step = chunk_images(n);
+	int total = 0, k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		cudaStream_t st = c->pipe[k % 3];
+		CK(cudaMemcpy2DAsync(c->d_src + i0 * img_dev, c->src_pitch, src + i0 * img_px, g.width, g.width,
+		                     (size_t)m * g.channels * g.height, cudaMemcpyHostToDevice, st));
+		c->img0 = i0;
+		rc = ric_encode_u8_device(c, c->d_src + i0 * img_dev, c->src_pitch, m, q, c->d_arena + i0 * img_ar, st);
+		c->img0 = 0;
+		if (rc) { sync_pipe(c); return rc; }
+		total += c->launches;
+		CK(cudaMemcpyAsync((char *)arenas + i0 * img_ar, c->d_arena + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyDeviceToHost, st));
+	}
+	c->launches = total;
+	return sync_pipe(c);
 }
 
 int ric_decode_u8(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst)
@@ -570,13 +597,24 @@ int ric_decode_u8(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst)
 	const HostGeom &g = c->g;
 	CK(cudaSetDevice(c->device));
 	if ((rc = need_arena_in(c))) return rc;
-	CK(cudaMemcpyAsync(c->d_arena_in, arenas, (size_t)n * g.channels * g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
-	rc = ric_decode_u8_device(c, c->d_arena_in, n, q, c->d_src, c->src_pitch, c->stream);
-	if (rc) return rc;
-	const size_t rows = (size_t)n * g.channels * g.height;
-	CK(cudaMemcpy2DAsync(dst, g.width, c->d_src, c->src_pitch, g.width, rows, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
-	return RIC_OK;
+	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	const int step = chunk_images(n);
+	int total = 0, k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		cudaStream_t st = c->pipe[k % 3];
+		CK(cudaMemcpyAsync(c->d_arena_in + i0 * img_ar, (const char *)arenas + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyHostToDevice, st));
+		c->img0 = i0;
+		rc = ric_decode_u8_device(c, c->d_arena_in + i0 * img_ar, m, q, c->d_src + i0 * img_dev, c->src_pitch, st);
+		c->img0 = 0;
+		if (rc) { sync_pipe(c); return rc; }
+		total += c->launches;
+		CK(cudaMemcpy2DAsync(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,
+		                     (size_t)m * g.channels * g.height, cudaMemcpyDeviceToHost, st));
+	}
+	c->launches = total;
+	return sync_pipe(c);
 }
 
 // ---- plane-level API (one plane, batch slot 0, plane slot 0) ------------------------------------

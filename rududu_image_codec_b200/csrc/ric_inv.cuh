@@ -44,7 +44,7 @@ struct InvParams {
 	int dq[3][4];              // TSUQi multiplier per plane for D,H,V,L (1 = no dequantisation)
 };
 
-__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }  // max(min(v, 255), 0), one VIMNMX.RELU
 
 // raw (not yet unpacked) inputs of one iteration: D/H row t, V/LL row t-1, 4 samples each
 template <bool SH>
@@ -258,15 +258,20 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 							int cg = (k & 1) ? (int)w1 >> 16 : (int)(short)(w1 & 0xFFFF);
 							int y = (k & 1) ? (int)w2 >> 16 : (int)(short)(w2 & 0xFFFF);
 							if (P.shift) {
-								co = (int)(short)((co + 4) >> 3);
-								cg = (int)(short)((cg + 4) >> 3);
-								y = (int)(short)((y + 8) >> 4);
+								// after the down-shifts every intermediate is < 2^14 in magnitude: the reference's
+								// short stores cannot wrap, so no truncation is needed on this path
+								co = (co + 4) >> 3; cg = (cg + 4) >> 3; y = (y + 8) >> 4;
+								y -= (cg >> 1) - 128;
+								cg += y;
+								y -= co >> 1;
+								co += y;
+								co = clip255(co); cg = clip255(cg); y = clip255(y);
+							} else {
+								y = (int)(short)(y - ((cg >> 1) - 128));
+								cg = (int)(short)(cg + y);
+								y = (int)(short)(y - (co >> 1));
+								co = (int)(short)(co + y);
 							}
-							y = (int)(short)(y - ((cg >> 1) - 128));
-							cg = (int)(short)(cg + y);
-							y = (int)(short)(y - (co >> 1));
-							co = (int)(short)(co + y);
-							if (P.shift) { co = clip255(co); cg = clip255(cg); y = clip255(y); }
 							R[k] = (unsigned)co & 0xFF; G[k] = (unsigned)cg & 0xFF; B[k] = (unsigned)y & 0xFF;
 						}
 						unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + (long long)row * P.dst_pitch + cb;
