@@ -190,16 +190,25 @@ static BandRef band_ref(const HostGeom &g, int id)
 	return r;
 }
 
-static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_images)
+// Rows per job.  Jobs are equal-sized and a launch runs in waves of `slots` concurrent jobs, so the
+// launch time is modelled as ceil(jobs / slots) waves x (seg/2 + 4) loop iterations per job (the +4
+// is the vertical warm-up); the segment height minimising that wins (ties: taller = less warm-up).
+static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_images, int jobs_per_sm)
 {
-	const int nstrips = (w + STRIP_W - 1) / STRIP_W;
-	int seg = 128;
-	while (seg > 16) {
-		const long long jobs = (long long)nstrips * ((h + seg - 1) / seg) * planes_images;
-		if (jobs >= c->target_warps) break;
-		seg >>= 1;
+	const long long nstrips = (w + STRIP_W - 1) / STRIP_W;
+	const long long slots = c->target_warps > 0 ? c->target_warps : (long long)c->sm_count * jobs_per_sm;
+	static const int cand[] = {256, 192, 160, 128, 112, 96, 80, 64, 56, 48, 40, 32, 24, 16};
+	int best = 16;
+	long long best_cost = -1;
+	for (int seg : cand) {
+		if (seg > 16 && seg >= 2 * ((h + 7) & ~7)) continue;  // taller than the level: same as a smaller candidate
+		const long long jobs = nstrips * ((h + seg - 1) / seg) * planes_images;
+		const long long waves = (jobs + slots - 1) / slots;
+		const int eff = seg < h ? seg : ((h + 7) & ~7);
+		const long long cost = waves * (eff / 2 + 4);
+		if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = seg; }
 	}
-	return seg;
+	return best;
 }
 
 extern "C" {
@@ -261,7 +270,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	CK(cudaGetDeviceProperties(&prop, device));
 	c->sm_count = prop.multiProcessorCount;
 	const char *tw = getenv("RIC_TARGET_WARPS");
-	c->target_warps = tw ? atoi(tw) : c->sm_count * 16;
+	c->target_warps = tw ? atoi(tw) : 0;  // override of the concurrent-job count used by choose_seg_rows
 #define CKD(call)                                                                    \
 	do {                                                                             \
 		cudaError_t e_ = (call);                                                     \
@@ -403,7 +412,7 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 		P.has_child = lv > 0;
 		P.w = g.lev_w[lv]; P.h = g.lev_h[lv];
 		P.nstrips = (P.w + STRIP_W - 1) / STRIP_W;
-		P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)nplanes * n);
+		P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)nplanes * n, 16);
 		P.nsegs = (P.h + P.seg_rows - 1) / P.seg_rows;
 		P.nplanes = nplanes; P.nimages = n;
 		P.shift = shift; P.quant = do_quant;
@@ -474,7 +483,7 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		P.w = g.lev_w[lv]; P.h = g.lev_h[lv];
 		P.nstrips = (P.w + STRIP_W - 1) / STRIP_W;
 		const int jplanes = dst == DST_U8_RGB ? 1 : nplanes;
-		P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)jplanes * n);
+		P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)jplanes * n, dst == DST_U8_RGB ? 6 : 16);
 		P.nsegs = (P.h + P.seg_rows - 1) / P.seg_rows;
 		P.nplanes = nplanes; P.nimages = n;
 		P.shift = shift;

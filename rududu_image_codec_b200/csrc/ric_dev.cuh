@@ -334,26 +334,41 @@ __device__ __forceinline__ int quant_block(int (&c)[16], const QuantBand *qb, in
 		cnt += (live && !cand) ? 1 : 0;
 		nc += cand ? 1 : 0;
 	}
-	if (__any_sync(__activemask(), nc > 0)) {
-		int s[16];
-#pragma unroll
-		for (int k = 0; k < 16; k++) s[k] = key[k];
-		sort16_desc(s);
+	const unsigned act = __activemask();
+	const int ncm = __reduce_max_sync(act, nc);  // largest candidate count among this warp's blocks
+	if (ncm > 0) {
 		int kstar = 0x7fffffff, m = 0;
-		if (qb->fast) {
-			const int *kt = qb->kthr + cnt;
+		if (ncm == 1) {
+			// at most one candidate per block (the common case on chroma planes): it is rank 0, so it
+			// survives iff f >= thr[cnt] -- no sort needed
+			int s0 = 0;
 #pragma unroll
-			for (int i = 0; i < 16; i++) {
-				const bool pass = s[i] >= kt[i];  // non-candidates (key 0) never pass: kthr > 0 whenever candidates exist
-				kstar = pass ? s[i] : kstar;
-				m = pass ? i + 1 : m;
-			}
+			for (int k = 0; k < 16; k++) s0 = max(s0, key[k]);
+			bool pass;
+			if (qb->fast) pass = s0 >= qb->kthr[cnt];
+			else pass = s0 != 0 && !(TR<SH>(s0 >> 4) < qb->thr[cnt & 15]);
+			if (pass && s0 != 0) { kstar = s0; m = 1; }
 		} else {
+			int s[16];
 #pragma unroll
-			for (int i = 0; i < 16; i++) {
-				if (s[i] != 0) {
-					const int fs = TR<SH>(s[i] >> 4);  // signed C compare, :191
-					if (!(fs < qb->thr[(cnt + i) & 15])) { kstar = s[i]; m = i + 1; }
+			for (int k = 0; k < 16; k++) s[k] = key[k];
+			sort16_desc(s);
+			if (qb->fast) {
+				const int *kt = qb->kthr + cnt;
+#pragma unroll
+				for (int i = 0; i < 16; i++) {
+					if ((i & 3) == 0 && i >= ncm) break;  // warp-uniform: ranks beyond the largest candidate count are empty
+					const bool pass = s[i] >= kt[i];  // non-candidates (key 0) never pass: kthr > 0 whenever candidates exist
+					kstar = pass ? s[i] : kstar;
+					m = pass ? i + 1 : m;
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < 16; i++) {
+					if (s[i] != 0) {
+						const int fs = TR<SH>(s[i] >> 4);  // signed C compare, :191
+						if (!(fs < qb->thr[(cnt + i) & 15])) { kstar = s[i]; m = i + 1; }
+					}
 				}
 			}
 		}
