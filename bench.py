@@ -300,7 +300,9 @@ def run_ours(args):
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get("fwd_level0_bytes_per_launch")
+                tj = json.load(open(traffic_file))  # ncu dram__bytes_read+write of this kernel on this workload
+                line["roofline"]["traffic"] = tj["fwd_level0_bytes_per_launch"] * S / tj["fwd_level0_samples_per_launch"]
+                line["roofline"]["traffic_source"] = "profiles/traffic.json (ncu --set full, scaled per sample to this batch)"
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:
