@@ -205,3 +205,53 @@ def test_ric_bitstream_bytes_from_gpu_bands(golden):
             arenas = c.encode_u8(img[None], q)
         payload = ref_payload_from_arenas(o, arenas, ch, k["trans"])
         assert (len(payload), crc(payload)) == (k["payload_bytes"], k["payload_crc"]), k
+
+
+@pytest.mark.parametrize("w,h", [(239, 40), (240, 40), (247, 33), (248, 33), (249, 64), (479, 24), (481, 24), (720, 135),
+                                  (2000, 16), (16, 2000), (65535, 16), (16, 65535)])
+def test_strip_and_segment_boundaries(w, h):
+    """Widths straddling the 240-column strip / 8-column lane grid, heights straddling segment and
+    4x4-block-row boundaries, extreme aspect ratios up to the u16 header limit (ric.cpp:150-153)."""
+    img = synth_image(7, w, h, 1)
+    o = oraclebind.Oracle(w, h, 5)
+    want = o.encode_image(img, 9)
+    with capi.Context(w, h, 1, 5) as c:
+        got = c.encode_u8(img[None], 9)
+        assert _diff(o, got, want) is None
+        o.unfold(want)
+        assert np.array_equal(c.decode_u8(want, 1, 9)[0], o.decode_image(want, 1, 9))
+
+
+@pytest.mark.parametrize("align", [32, 64, 128])
+def test_alignments(align):
+    w, h = 250, 130
+    rng = np.random.default_rng(align)
+    plane = rng.integers(-32768, 32768, size=(h, w), dtype=np.int16)
+    o = oraclebind.Oracle(w, h, 5, 1, align=align)
+    with capi.Context(w, h, 1, 5, 1, align=align) as c:
+        got = c.transform(plane)
+        assert _diff(o, got, o.forward(plane)) is None
+        assert np.array_equal(c.transform_inv(got), plane)  # lossless identity of the 9/7 lifting
+
+
+def test_device_api_with_padded_pitch():
+    """ric_*_device with a caller pitch larger than the width (rows padded to 512 bytes)."""
+    import torch
+    w, h, ch, q, pitch = 333, 77, 3, 9, 512
+    img = synth_image(2, w, h, ch)
+    o = oraclebind.Oracle(w, h, 5)
+    want = o.encode_image(img, q)
+    with capi.Context(w, h, ch, 5) as c:
+        src = torch.zeros((ch, h, pitch), dtype=torch.uint8, device="cuda")
+        src[:, :, :w] = torch.from_numpy(img).cuda()
+        ar = torch.zeros(c.image_arena_bytes, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        c.encode_u8_device(src.data_ptr(), pitch, 1, q, ar.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert np.array_equal(ar.cpu().numpy(), want)
+        for p in range(ch):
+            o.unfold(want[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+        dst = torch.zeros((ch, h, pitch), dtype=torch.uint8, device="cuda")
+        c.decode_u8_device(torch.from_numpy(want).cuda().data_ptr(), 1, q, dst.data_ptr(), pitch, st)
+        torch.cuda.synchronize()
+        assert np.array_equal(dst[:, :, :w].cpu().numpy(), o.decode_image(want, ch, q))
