@@ -144,10 +144,12 @@ __device__ __forceinline__ EdgeX make_edge_x(int cb, int w, bool on)
 	return e;
 }
 
-template <bool SH, int TRANS, bool NT = false>
-__device__ __forceinline__ void row_fwd(int (&v)[8], const EdgeX &e)
+template <bool SH, int TRANS, bool NT, bool EDGE>
+__device__ __forceinline__ void row_fwd(int (&v)[8], const EdgeX &ee)
 {
 	constexpr bool S = SH && !NT;
+	EdgeX e = ee;
+	if (!EDGE) e.on = false;  // interior strips: every fix-up below folds away at compile time
 	int nl, nr, o[8];
 	// S1: even columns
 	nl = __shfl_up_sync(FULL, v[7], 1);
@@ -190,9 +192,11 @@ __device__ __forceinline__ void row_fwd(int (&v)[8], const EdgeX &e)
 	}
 }
 
-template <bool SH, int TRANS>
-__device__ __forceinline__ void row_inv(int (&v)[8], const EdgeX &e)
+template <bool SH, int TRANS, bool EDGE>
+__device__ __forceinline__ void row_inv(int (&v)[8], const EdgeX &ee)
 {
+	EdgeX e = ee;
+	if (!EDGE) e.on = false;  // interior strips: every fix-up below folds away at compile time
 	int nl, nr, o[8];
 	if (TRANS == T97) {
 		// U4: odd columns

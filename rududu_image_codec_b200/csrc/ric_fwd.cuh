@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 			const int rn = r + 1;
 			load_raw<SRC>(raw, src, (long long)rn * P.src_pitch, cb, col_ok && rn >= 0 && rn < h, P.src_plane_stride, plane);
 		}
-		row_fwd<SH, TRANS, NT>(no, ex);
+		if (ex.on) row_fwd<SH, TRANS, NT, true>(no, ex); else row_fwd<SH, TRANS, NT, false>(no, ex);
 		if (!(r & 1)) {
 #pragma unroll
 			for (int k = 0; k < 8; k++) ne[k] = no[k];

@@ -139,7 +139,9 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 {
 	constexpr bool RGB = DST == DST_U8_RGB;
 	// RGB staging: [group][slot][plane][row parity][lane] -> 8 s16 samples
-	__shared__ uint4 s_stage[RGB ? INV_RGB_GROUPS : 1][RGB ? 3 : 1][RGB ? 3 : 1][RGB ? 2 : 1][RGB ? 32 : 1];
+	// double-buffered (set = batch parity): one barrier per batch of three iterations is enough, because a
+	// set is rewritten only after every warp of the group has passed the barrier that follows its last reads
+	__shared__ uint4 s_stage[RGB ? INV_RGB_GROUPS : 1][RGB ? 2 : 1][RGB ? 3 : 1][RGB ? 3 : 1][RGB ? 2 : 1][RGB ? 32 : 1];
 
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int grp = RGB ? wib / 3 : 0;
@@ -196,15 +198,16 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 		// finished: even row r1 (se3), odd row r2 (so4); both rows' horizontal passes are unrolled so
 		// that their dependency chains interleave (this kernel fits the instruction cache either way)
 		const int slot = RGB ? (t - t_begin) % 3 : 0;
+		const int set = RGB ? ((t - t_begin) / 3) & 1 : 0;
 #pragma unroll
 		for (int half = 0; half < 2; half++) {
 			int o[8];
 #pragma unroll
 			for (int k = 0; k < 8; k++) o[k] = half ? so4[k] : se3[k];
-			row_inv<SH, TRANS>(o, ex);
+			if (ex.on) row_inv<SH, TRANS, true>(o, ex); else row_inv<SH, TRANS, false>(o, ex);
 			const int row = half ? r2 : r1;
 			if (DST == DST_U8_RGB) {
-				s_stage[grp][slot][plane][half][lane] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+				s_stage[grp][set][slot][plane][half][lane] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
 				continue;
 			}
 			if (!(row >= y0 && row < y1 && lane_out)) continue;
@@ -246,8 +249,8 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 					for (int half = 0; half < 2; half++) {
 						const int row = half ? 2 * tt - 3 : 2 * tt - 4;
 						if (!(row >= y0 && row < y1 && lane_out)) continue;
-						const uint4 c0 = s_stage[grp][my][0][half][lane], c1 = s_stage[grp][my][1][half][lane],
-						            c2 = s_stage[grp][my][2][half][lane];
+						const uint4 c0 = s_stage[grp][set][my][0][half][lane], c1 = s_stage[grp][set][my][1][half][lane],
+						            c2 = s_stage[grp][set][my][2][half][lane];
 						unsigned R[8], G[8], B[8];
 #pragma unroll
 						for (int k = 0; k < 8; k++) {  // YCoCgtoRGB<shift>, ric.cpp:93-112 (planes 0 Co, 1 Cg, 2 Y)
@@ -280,7 +283,6 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 						*(uint2 *)(dp + 2 * P.dst_plane_stride) = make_uint2(pack4b(B[0], B[1], B[2], B[3]), pack4b(B[4], B[5], B[6], B[7]));
 					}
 				}
-				asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory");
 			}
 		}
 	}
