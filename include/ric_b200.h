@@ -90,6 +90,20 @@ int ric_plane_quant(int q, int channels, int plane, int *Quant, int *lambda);
 int ric_encode_u8(ric_ctx *ctx, const uint8_t *src, int n, int q, void *arenas);
 int ric_decode_u8(ric_ctx *ctx, const void *arenas, int n, int q, uint8_t *dst);
 
+/* ---- streaming variants: overlap with host entropy threads ------------------------------------
+ * ric_encode_u8_stream returns as soon as every chunk of the batch is enqueued (H2D, kernels, D2H
+ * alternate over three internal streams).  `done(user, first_image, n_images)` is called once per
+ * chunk, from a CUDA callback thread, when the arenas of those images have landed in `arenas`
+ * (use pinned memory, ric_host_alloc): the callback must not call CUDA or ric_* functions -- it
+ * hands the chunk to a host worker, e.g. one running the reference's entropy half of CodeBand
+ * (wavelet2d.cpp:119-159) while the GPU works on the next chunk.  ric_sync waits for everything.
+ * ric_decode_u8_stream is the mirror image (done fires when the pixels of a chunk are in `dst`).
+ * ric_encode_u8 / ric_decode_u8 are these calls followed by ric_sync. */
+typedef void (*ric_chunk_fn)(void *user, int first_image, int n_images);
+int ric_encode_u8_stream(ric_ctx *ctx, const uint8_t *src, int n, int q, void *arenas, ric_chunk_fn done, void *user);
+int ric_decode_u8_stream(ric_ctx *ctx, const void *arenas, int n, int q, uint8_t *dst, ric_chunk_fn done, void *user);
+int ric_sync(ric_ctx *ctx);
+
 /* ---- device-resident variants (no copies; asynchronous on `stream`, a cudaStream_t) ------------
  * d_src pitch: bytes between rows (multiple of 8); planes are pitch*height apart, images
  * channels*pitch*height apart.  d_arenas as above but in device memory.  d_dst likewise. */

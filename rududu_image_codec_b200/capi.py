@@ -22,6 +22,7 @@ EXPORTS = [
     "ric_plane_quant", "ric_encode_u8", "ric_decode_u8", "ric_encode_u8_device", "ric_decode_u8_device",
     "ric_last_launch_count", "ric_transform", "ric_quant", "ric_tsuq", "ric_tsuqi", "ric_transform_inv",
     "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times",
+    "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync",
 ]
 
 
@@ -42,6 +43,8 @@ class Info(C.Structure):
                 ("nbands", C.c_int), ("max_batch", C.c_int), ("arena_bytes", C.c_size_t),
                 ("image_arena_bytes", C.c_size_t)]
 
+
+CHUNK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int)  # ric_chunk_fn
 
 _lib = None
 
@@ -75,6 +78,9 @@ def lib():
         L.ric_host_alloc.argtypes = [C.POINTER(vp), sz]
         L.ric_host_free.argtypes = [vp]
         L.ric_set_profiling.argtypes = [vp, i]
+        L.ric_encode_u8_stream.argtypes = [vp, vp, i, i, vp, CHUNK_FN, vp]
+        L.ric_decode_u8_stream.argtypes = [vp, vp, i, i, vp, CHUNK_FN, vp]
+        L.ric_sync.argtypes = [vp]
         L.ric_get_level_times.argtypes = [vp, i, C.POINTER(C.c_float), i]
         _lib = L
     return _lib
@@ -162,6 +168,20 @@ class Context:
             out = np.empty((n, self.channels, self.height, self.width), dtype=np.uint8)
         _check(self.L.ric_decode_u8(self.h, _ptr(arenas), n, q, _ptr(out)))
         return out
+
+    def encode_u8_stream(self, imgs, q, out, done):
+        """Asynchronous encode: `done(first_image, n_images)` fires per chunk once its arenas are in `out`
+        (called on a CUDA callback thread).  Call sync() before reusing the buffers."""
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8).reshape(-1, self.channels, self.height, self.width)
+        self._keep = (imgs, out, CHUNK_FN(lambda user, first, cnt: done(first, cnt)))
+        _check(self.L.ric_encode_u8_stream(self.h, _ptr(imgs), imgs.shape[0], q, _ptr(out), self._keep[2], None))
+
+    def decode_u8_stream(self, arenas, n, q, out, done):
+        self._keep = (arenas, out, CHUNK_FN(lambda user, first, cnt: done(first, cnt)))
+        _check(self.L.ric_decode_u8_stream(self.h, _ptr(arenas), n, q, _ptr(out), self._keep[2], None))
+
+    def sync(self):
+        _check(self.L.ric_sync(self.h))
 
     # ---- device-resident variants (pointers are raw device addresses, stream a cudaStream_t) ----
     def encode_u8_device(self, d_src, pitch, n, q, d_arenas, stream=0):

@@ -37,6 +37,8 @@ struct ric_ctx {
 	int sm_count;
 	cudaStream_t stream;
 	cudaStream_t pipe[3];    // host-buffer calls: chunks of the batch alternate over these (copy/compute overlap)
+	struct ChunkNote { ric_chunk_fn fn; void *user; int first, count; };
+	std::vector<ChunkNote> notes;  // one per chunk of the last *_stream call (must outlive the callbacks)
 	int img0;                // first image slot used by the launch functions (chunked pipelining)
 	// device buffers
 	unsigned char *d_src;   // [max_batch][channels][height][src_pitch] u8
@@ -262,7 +264,6 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	CK(cudaSetDevice(device));
 	ric_ctx *c = new (std::nothrow) ric_ctx();
 	if (!c) return set_err(RIC_E_NOMEM, "ric_create: out of host memory");
-	memset(c, 0, sizeof *c);
 	c->g = g;
 	c->device = device;
 	c->max_batch = max_batch;
@@ -571,16 +572,31 @@ static int sync_pipe(ric_ctx *c)
 	return RIC_OK;
 }
 
-int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
+static void CUDART_CB chunk_trampoline(void *p)
 {
-	int rc = check_batch(c, n, q, "ric_encode_u8");
+	ric_ctx::ChunkNote *n = (ric_ctx::ChunkNote *)p;
+	n->fn(n->user, n->first, n->count);
+}
+
+int ric_sync(ric_ctx *c)
+{
+	if (!c) return set_err(RIC_E_ARG, "ric_sync: null context");
+	CK(cudaSetDevice(c->device));
+	return sync_pipe(c);
+}
+
+int ric_encode_u8_stream(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas, ric_chunk_fn done, void *user)
+{
+	int rc = check_batch(c, n, q, "ric_encode_u8_stream");
 	if (rc) return rc;
-	if (!src || !arenas) return set_err(RIC_E_ARG, "ric_encode_u8: null buffer");
+	if (!src || !arenas) return set_err(RIC_E_ARG, "ric_encode_u8_stream: null buffer");
 	const HostGeom &g = c->g;
 	CK(cudaSetDevice(c->device));
+	if ((rc = sync_pipe(c))) return rc;  // the previous call's chunk notes are about to be reused
 	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
 	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
 	const int step = chunk_images(n);
+	c->notes.assign((size_t)(n + step - 1) / step, ric_ctx::ChunkNote{done, user, 0, 0});
 	int total = 0, k = 0;
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
@@ -593,22 +609,35 @@ int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
 		if (rc) { sync_pipe(c); return rc; }
 		total += c->launches;
 		CK(cudaMemcpyAsync((char *)arenas + i0 * img_ar, c->d_arena + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyDeviceToHost, st));
+		if (done) {
+			c->notes[k].first = i0;
+			c->notes[k].count = m;
+			CK(cudaLaunchHostFunc(st, chunk_trampoline, &c->notes[k]));
+		}
 	}
 	c->launches = total;
-	return sync_pipe(c);
+	return RIC_OK;
 }
 
-int ric_decode_u8(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst)
+int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
 {
-	int rc = check_batch(c, n, q, "ric_decode_u8");
+	int rc = ric_encode_u8_stream(c, src, n, q, arenas, nullptr, nullptr);
+	return rc ? rc : sync_pipe(c);
+}
+
+int ric_decode_u8_stream(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst, ric_chunk_fn done, void *user)
+{
+	int rc = check_batch(c, n, q, "ric_decode_u8_stream");
 	if (rc) return rc;
-	if (!dst || !arenas) return set_err(RIC_E_ARG, "ric_decode_u8: null buffer");
+	if (!dst || !arenas) return set_err(RIC_E_ARG, "ric_decode_u8_stream: null buffer");
 	const HostGeom &g = c->g;
 	CK(cudaSetDevice(c->device));
 	if ((rc = need_arena_in(c))) return rc;
+	if ((rc = sync_pipe(c))) return rc;
 	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
 	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
 	const int step = chunk_images(n);
+	c->notes.assign((size_t)(n + step - 1) / step, ric_ctx::ChunkNote{done, user, 0, 0});
 	int total = 0, k = 0;
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
@@ -621,9 +650,20 @@ int ric_decode_u8(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst)
 		total += c->launches;
 		CK(cudaMemcpy2DAsync(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,
 		                     (size_t)m * g.channels * g.height, cudaMemcpyDeviceToHost, st));
+		if (done) {
+			c->notes[k].first = i0;
+			c->notes[k].count = m;
+			CK(cudaLaunchHostFunc(st, chunk_trampoline, &c->notes[k]));
+		}
 	}
 	c->launches = total;
-	return sync_pipe(c);
+	return RIC_OK;
+}
+
+int ric_decode_u8(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst)
+{
+	int rc = ric_decode_u8_stream(c, arenas, n, q, dst, nullptr, nullptr);
+	return rc ? rc : sync_pipe(c);
 }
 
 // ---- plane-level API (one plane, batch slot 0, plane slot 0) ------------------------------------

@@ -50,3 +50,23 @@ def test_shim_matches_oracle(tmp_path, w, h):
     assert np.array_equal(np.fromfile(tmp_path / "arena.bin", dtype=np.uint8), want)
     o.tsuqi(signed, Quant)
     assert np.array_equal(np.fromfile(tmp_path / "out.s16", dtype=np.int16).reshape(h, w), o.inverse(signed))
+
+
+@pytest.mark.gpu
+def test_streaming_pipeline_with_reference_entropy_coder(tmp_path):
+    """configs[3] in miniature: GPU encode of a batch overlapped with host threads running the
+    reference's own entropy coder on the chunks as they land; every .ric payload must equal the
+    reference's monolithic CompressImage output."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "libric_ref.so")):
+        pytest.skip("oracle/_ref not built")
+    exe = str(tmp_path / "pipeline_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "pipeline_test.cpp"), "-L" + PKG, "-lrududu_b200",
+                           "-L" + ref_dir, "-lric_ref", "-Wl,-rpath," + PKG, "-Wl,-rpath," + ref_dir])
+    w, h, n, q = 480, 272, 13, 9
+    imgs = np.stack([synth_image(i, w, h, 3) for i in range(n)])
+    imgs.tofile(tmp_path / "imgs.u8")
+    r = subprocess.run([exe, str(w), str(h), str(n), str(q), str(tmp_path / "imgs.u8")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("ok")

@@ -255,3 +255,34 @@ def test_device_api_with_padded_pitch():
         c.decode_u8_device(torch.from_numpy(want).cuda().data_ptr(), 1, q, dst.data_ptr(), pitch, st)
         torch.cuda.synchronize()
         assert np.array_equal(dst[:, :, :w].cpu().numpy(), o.decode_image(want, ch, q))
+
+
+def test_stream_api_chunk_callbacks():
+    """ric_encode_u8_stream / ric_decode_u8_stream: every chunk's data is complete when its callback fires."""
+    w, h, ch, n, q = 320, 200, 3, 9, 9
+    imgs = np.stack([synth_image(i, w, h, ch) for i in range(n)])
+    o = oraclebind.Oracle(w, h, 5)
+    want = [o.encode_image(imgs[i], q) for i in range(n)]
+    with capi.Context(w, h, ch, 5, max_batch=n) as c:
+        out = np.zeros(n * c.image_arena_bytes, dtype=np.uint8)
+        seen, ok = [], []
+
+        def done(first, cnt):
+            seen.append((first, cnt))
+            for i in range(first, first + cnt):
+                ok.append(np.array_equal(out[i * c.image_arena_bytes:(i + 1) * c.image_arena_bytes], want[i]))
+
+        c.encode_u8_stream(imgs, q, out, done)
+        c.sync()
+        assert sorted(i for f, k in seen for i in range(f, f + k)) == list(range(n))
+        assert len(seen) > 1 and all(ok) and len(ok) == n
+        signed = out.copy()
+        for i in range(n * ch):
+            o.unfold(signed[i * o.arena_bytes:(i + 1) * o.arena_bytes])
+        dec = np.zeros((n, ch, h, w), dtype=np.uint8)
+        seen2 = []
+        c.decode_u8_stream(signed, n, q, dec, lambda f, k: seen2.append((f, k)))
+        c.sync()
+        assert sum(k for _, k in seen2) == n
+        for i in range(n):
+            assert np.array_equal(dec[i], o.decode_image(signed[i * c.image_arena_bytes:(i + 1) * c.image_arena_bytes], ch, q))
