@@ -284,7 +284,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 3; i++) CKD(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
 	const size_t nb = (size_t)max_batch, ch = (size_t)channels;
-	c->src_pitch = ((size_t)width + 7 + 8) & ~(size_t)7;  // >= roundup8(w), one spare vector
+	c->src_pitch = ((size_t)width + 7) & ~(size_t)7;  // roundup8(w): dense rows (one contiguous copy) when w % 8 == 0
 	CKD(cudaMalloc(&c->d_src, nb * ch * height * c->src_pitch + 64));
 	CKD(cudaMalloc(&c->d_arena, nb * ch * g.arena_bytes + 64));
 	CKD(cudaMemset(c->d_arena, 0, nb * ch * g.arena_bytes + 64));  // padding columns stay zero
@@ -564,6 +564,13 @@ int ric_decode_u8_device(ric_ctx *c, const void *d_arenas, int n, int q, uint8_t
 // Host-buffer entry points: the batch is cut into chunks that alternate over three streams, so the
 // H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap (each chunk
 // owns its image slots of every device buffer, LL scratch and flags included).
+static cudaError_t copy_pixels(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                               cudaMemcpyKind kind, cudaStream_t st)
+{
+	if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+	return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+}
+
 static int chunk_images(int n) { return n >= 12 ? (n + 7) / 8 : n >= 4 ? 2 : 1; }
 
 static int sync_pipe(ric_ctx *c)
@@ -601,8 +608,8 @@ int ric_encode_u8_stream(ric_ctx *c, const uint8_t *src, int n, int q, void *are
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
 		cudaStream_t st = c->pipe[k % 3];
-		CK(cudaMemcpy2DAsync(c->d_src + i0 * img_dev, c->src_pitch, src + i0 * img_px, g.width, g.width,
-		                     (size_t)m * g.channels * g.height, cudaMemcpyHostToDevice, st));
+		CK(copy_pixels(c->d_src + i0 * img_dev, c->src_pitch, src + i0 * img_px, g.width, g.width,
+		               (size_t)m * g.channels * g.height, cudaMemcpyHostToDevice, st));
 		c->img0 = i0;
 		rc = ric_encode_u8_device(c, c->d_src + i0 * img_dev, c->src_pitch, m, q, c->d_arena + i0 * img_ar, st);
 		c->img0 = 0;
@@ -648,8 +655,8 @@ int ric_decode_u8_stream(ric_ctx *c, const void *arenas, int n, int q, uint8_t *
 		c->img0 = 0;
 		if (rc) { sync_pipe(c); return rc; }
 		total += c->launches;
-		CK(cudaMemcpy2DAsync(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,
-		                     (size_t)m * g.channels * g.height, cudaMemcpyDeviceToHost, st));
+		CK(copy_pixels(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,
+		               (size_t)m * g.channels * g.height, cudaMemcpyDeviceToHost, st));
 		if (done) {
 			c->notes[k].first = i0;
 			c->notes[k].count = m;
