@@ -52,6 +52,8 @@ struct ric_ctx {
 	int ll_pitch[RIC_MAX_LEVELS];
 	int ll_es[RIC_MAX_LEVELS];
 	unsigned *d_count;
+	unsigned long long *d_jobctr;        // job counters of the persistent kernels: [4 stream sets][2 directions][levels]
+	int cset;                            // counter set in use (0-2: internal pipeline streams, 3: caller's stream)
 	int launches;
 	int profiling;                       // record CUDA events around every level launch
 	cudaEvent_t ev[2][RIC_MAX_LEVELS + 1];  // [direction][launch boundary]
@@ -192,9 +194,9 @@ static BandRef band_ref(const HostGeom &g, int id)
 	return r;
 }
 
-// Rows per job.  Jobs are equal-sized and a launch runs in waves of `slots` concurrent jobs, so the
-// launch time is modelled as ceil(jobs / slots) waves x (seg/2 + 4) loop iterations per job (the +4
-// is the vertical warm-up); the segment height minimising that wins (ties: taller = less warm-up).
+// Rows per job.  Jobs are equal-sized and claimed dynamically by persistent CTAs, so a launch takes
+// about (total loop iterations / concurrent jobs) + one job (the tail); a job of `seg` rows runs
+// seg/2 + 4 iterations (the +4 is the vertical warm-up).  The segment height minimising that wins.
 static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_images, int jobs_per_sm)
 {
 	const long long nstrips = (w + STRIP_W - 1) / STRIP_W;
@@ -204,10 +206,11 @@ static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_imag
 	long long best_cost = -1;
 	for (int seg : cand) {
 		if (seg > 16 && seg >= 2 * ((h + 7) & ~7)) continue;  // taller than the level: same as a smaller candidate
-		const long long jobs = nstrips * ((h + seg - 1) / seg) * planes_images;
-		const long long waves = (jobs + slots - 1) / slots;
-		const int eff = seg < h ? seg : ((h + 7) & ~7);
-		const long long cost = waves * (eff / 2 + 4);
+		const long long nseg = (h + seg - 1) / seg, rem = h - (nseg - 1) * seg;  // last segment may be short
+		const long long it = (seg < h ? seg : ((h + 7) & ~7)) / 2 + 4, it_last = ((rem + 7) & ~7) / 2 + 4;
+		const long long cols = nstrips * planes_images;          // independent columns of segments
+		const long long jobs = cols * nseg, work = cols * ((nseg - 1) * it + it_last);
+		const long long cost = jobs <= slots ? 2 * it : 2 * ((work + slots - 1) / slots) + it;  // (x2: half-job tail)
 		if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = seg; }
 	}
 	return best;
@@ -237,6 +240,7 @@ int ric_destroy(ric_ctx *c)
 	cudaFree(c->d_flags);
 	cudaFree(c->d_plane);
 	cudaFree(c->d_count);
+	cudaFree(c->d_jobctr);
 	for (int d = 0; d < 2; d++)
 		for (int i = 0; i <= RIC_MAX_LEVELS; i++)
 			if (c->ev[d][i]) cudaEventDestroy(c->ev[d][i]);
@@ -300,6 +304,8 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 		CKD(cudaMemset(c->d_ll[i], 0, bytes));
 	}
 	CKD(cudaMalloc(&c->d_count, sizeof(unsigned)));
+	CKD(cudaMalloc(&c->d_jobctr, 4 * 2 * RIC_MAX_LEVELS * sizeof(unsigned long long)));
+	c->cset = 3;
 	for (int d = 0; d < 2; d++)
 		for (int i = 0; i <= g.nlev; i++) CKD(cudaEventCreate(&c->ev[d][i]));
 	CKD(cudaDeviceSynchronize());
@@ -375,6 +381,8 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 	const HostGeom &g = c->g;
 	c->launches = 0;
 	c->ev_n[0] = 0;
+	unsigned long long *ctr = c->d_jobctr + (size_t)(c->cset * 2 + 0) * RIC_MAX_LEVELS;
+	CK(cudaMemsetAsync(ctr, 0, RIC_MAX_LEVELS * sizeof(unsigned long long), st));
 	if (c->profiling) { CK(cudaEventRecord(c->ev[0][0], st)); }
 	for (int lv = 0; lv < g.nlev; lv++) {
 		FwdParams P;
@@ -433,7 +441,8 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 		if (!fn) return set_err(RIC_E_UNSUPPORTED, "forward: unsupported level type combination");
 		const long long njobs = (long long)P.nstrips * P.nsegs * nplanes * n;
 		const int wpb = fwd_warps(sh);
-		const unsigned grid = (unsigned)((njobs + wpb - 1) / wpb);
+		P.counter = ctr + lv;
+		const unsigned grid = (unsigned)std::min<long long>((njobs + wpb - 1) / wpb, (long long)c->sm_count * 4);
 		fn<<<grid, wpb * 32, 0, st>>>(P);
 		CK(cudaGetLastError());
 		c->launches++;
@@ -450,6 +459,8 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 	const HostGeom &g = c->g;
 	c->launches = 0;
 	c->ev_n[1] = 0;
+	unsigned long long *ctr = c->d_jobctr + (size_t)(c->cset * 2 + 1) * RIC_MAX_LEVELS;
+	CK(cudaMemsetAsync(ctr, 0, RIC_MAX_LEVELS * sizeof(unsigned long long), st));
 	if (c->profiling) { CK(cudaEventRecord(c->ev[1][0], st)); }
 	for (int lv = g.nlev - 1; lv >= 0; lv--) {
 		InvParams P;
@@ -496,11 +507,12 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		inv_fn fn = pick_inv(sh, g.trans, dst);
 		if (!fn) return set_err(RIC_E_UNSUPPORTED, "inverse: unsupported level type combination");
 		const long long njobs = (long long)P.nstrips * P.nsegs * jplanes * n;
+		P.counter = ctr + lv;
 		if (dst == DST_U8_RGB) {
-			const unsigned grid = (unsigned)((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS);
+			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * 3);
 			fn<<<grid, INV_RGB_GROUPS * 96, 0, st>>>(P);
 		} else {
-			const unsigned grid = (unsigned)((njobs + INV_WARPS - 1) / INV_WARPS);
+			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_WARPS - 1) / INV_WARPS, (long long)c->sm_count * 4);
 			fn<<<grid, INV_WARPS * 32, 0, st>>>(P);
 		}
 		CK(cudaGetLastError());
@@ -611,8 +623,10 @@ int ric_encode_u8_stream(ric_ctx *c, const uint8_t *src, int n, int q, void *are
 		CK(copy_pixels(c->d_src + i0 * img_dev, c->src_pitch, src + i0 * img_px, g.width, g.width,
 		               (size_t)m * g.channels * g.height, cudaMemcpyHostToDevice, st));
 		c->img0 = i0;
+		c->cset = k % 3;
 		rc = ric_encode_u8_device(c, c->d_src + i0 * img_dev, c->src_pitch, m, q, c->d_arena + i0 * img_ar, st);
 		c->img0 = 0;
+		c->cset = 3;
 		if (rc) { sync_pipe(c); return rc; }
 		total += c->launches;
 		CK(cudaMemcpyAsync((char *)arenas + i0 * img_ar, c->d_arena + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyDeviceToHost, st));
@@ -651,8 +665,10 @@ int ric_decode_u8_stream(ric_ctx *c, const void *arenas, int n, int q, uint8_t *
 		cudaStream_t st = c->pipe[k % 3];
 		CK(cudaMemcpyAsync(c->d_arena_in + i0 * img_ar, (const char *)arenas + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyHostToDevice, st));
 		c->img0 = i0;
+		c->cset = k % 3;
 		rc = ric_decode_u8_device(c, c->d_arena_in + i0 * img_ar, m, q, c->d_src + i0 * img_dev, c->src_pitch, st);
 		c->img0 = 0;
+		c->cset = 3;
 		if (rc) { sync_pipe(c); return rc; }
 		total += c->launches;
 		CK(copy_pixels(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,

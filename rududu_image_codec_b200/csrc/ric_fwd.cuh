@@ -58,6 +58,7 @@ struct FwdParams {
 	int plane_class[3];        // quantiser class of each plane (0 luma / 1 chroma)
 	QuantBand qb[2][3];        // [class][orientation]
 	int llQ[2], lliQ[2], llT[2];  // LL TSUQ scalars per class
+	unsigned long long *counter;  // dynamic job fetch (zeroed before the launch)
 };
 
 template <int SRC>
@@ -238,25 +239,15 @@ __device__ __forceinline__ void flush_blocks(const FwdParams &P, const Ring<SH> 
 	}
 }
 
+// One job = one (image, plane, row segment, strip); see the header comment.
 template <bool SH, int TRANS, int SRC>
-__global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const __grid_constant__ FwdParams P)
+__device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<SH> &rg, const QuantBand (&s_qb)[2][3], int lane)
 {
-	__shared__ QuantBand s_qb[2][3];
-	constexpr int FWD_WARPS = fwd_warps(SH);
-	__shared__ Ring<SH> s_ring[FWD_WARPS];
-	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
-	__syncthreads();
-
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	long long job = (long long)blockIdx.x * FWD_WARPS + wib;
-	const long long njobs = (long long)P.nstrips * P.nplanes * P.nsegs * P.nimages;
-	if (job >= njobs) return;
 	// plane fastest: the planes of one RGB strip share their u8 loads through L1
 	const int plane = (int)(job % P.nplanes); job /= P.nplanes;
 	const int sx = (int)(job % P.nstrips); job /= P.nstrips;
 	const int sy = (int)(job % P.nsegs);
 	const int img = (int)(job / P.nsegs);
-	Ring<SH> &rg = s_ring[wib];
 
 	const int w = P.w, h = P.h;
 	const int x0 = sx * STRIP_W;
@@ -375,6 +366,29 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 		// rotate the vertical state
 #pragma unroll
 		for (int k = 0; k < 8; k++) { se3[k] = se1[k]; so2[k] = so1[k]; se1[k] = ne[k]; so1[k] = no[k]; }
+	}
+}
+
+// Persistent CTAs: each CTA repeatedly claims the next FWD_WARPS consecutive jobs (one per warp) from a
+// global counter, so a launch has no wave-quantisation tail beyond one job; consecutive jobs (the
+// planes of one strip) stay in one CTA and keep sharing their pixel loads through L1.
+template <bool SH, int TRANS, int SRC>
+__global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const __grid_constant__ FwdParams P)
+{
+	constexpr int FWD_WARPS = fwd_warps(SH);
+	__shared__ QuantBand s_qb[2][3];
+	__shared__ Ring<SH> s_ring[FWD_WARPS];
+	__shared__ unsigned long long s_base;
+	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const long long njobs = (long long)P.nstrips * P.nplanes * P.nsegs * P.nimages;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) s_base = atomicAdd(P.counter, (unsigned long long)FWD_WARPS);
+		__syncthreads();
+		const long long base = (long long)s_base;
+		if (base >= njobs) break;
+		if (base + wib < njobs) fwd_job<SH, TRANS, SRC>(P, base + wib, s_ring[wib], s_qb, lane);
 	}
 }
 

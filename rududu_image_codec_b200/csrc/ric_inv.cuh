@@ -42,6 +42,7 @@ struct InvParams {
 	int nstrips, nsegs, seg_rows, nplanes, nimages;
 	int shift;                 // q != 0: undo the fixed-point up-shift and clip (ric.cpp:98-110,237-240)
 	int dq[3][4];              // TSUQi multiplier per plane for D,H,V,L (1 = no dequantisation)
+	unsigned long long *counter;  // dynamic job fetch (zeroed before the launch)
 };
 
 __device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }  // max(min(v, 255), 0), one VIMNMX.RELU
@@ -132,24 +133,20 @@ __device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &
 __device__ __forceinline__ unsigned pack2(int a, int b) { return (unsigned)(a & 0xFFFF) | ((unsigned)b << 16); }
 __device__ __forceinline__ unsigned pack4b(unsigned a, unsigned b, unsigned c, unsigned d) { return a | b << 8 | c << 16 | d << 24; }
 
+// RGB staging: [set][slot][plane][row parity][lane] -> 8 s16 samples.  Double-buffered (set = batch
+// parity): one barrier per batch of three iterations is enough, because a set is rewritten only after
+// every warp of the group has passed the barrier that follows its last reads.
+typedef uint4 RgbStage[2][3][3][2][32];
+
+// One job = one (image, row segment, strip) of one plane -- or, for RGB output, of all three planes
+// (the three warps of a group run the same job with plane = their index in the group).
 // SH: this level works on short; DST: what is written.
 template <bool SH, int TRANS, int DST>
-__global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_WARPS * 32, DST == DST_U8_RGB ? 3 : 4)
-    inv_level_kernel(const __grid_constant__ InvParams P)
+__device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbStage *stage, int grp, int wig, int lane)
 {
 	constexpr bool RGB = DST == DST_U8_RGB;
-	// RGB staging: [group][slot][plane][row parity][lane] -> 8 s16 samples
-	// double-buffered (set = batch parity): one barrier per batch of three iterations is enough, because a
-	// set is rewritten only after every warp of the group has passed the barrier that follows its last reads
-	__shared__ uint4 s_stage[RGB ? INV_RGB_GROUPS : 1][RGB ? 2 : 1][RGB ? 3 : 1][RGB ? 3 : 1][RGB ? 2 : 1][RGB ? 32 : 1];
-
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int grp = RGB ? wib / 3 : 0;
-	long long job = RGB ? (long long)blockIdx.x * INV_RGB_GROUPS + grp : (long long)blockIdx.x * INV_WARPS + wib;
 	const int jplanes = RGB ? 1 : P.nplanes;
-	const long long njobs = (long long)P.nstrips * jplanes * P.nsegs * P.nimages;
-	if (job >= njobs) return;  // RGB: the three warps of a group leave together
-	const int plane = RGB ? wib % 3 : (int)(job % jplanes);
+	const int plane = RGB ? wig : (int)(job % jplanes);
 	job /= jplanes;
 	const int sx = (int)(job % P.nstrips); job /= P.nstrips;
 	const int sy = (int)(job % P.nsegs);
@@ -207,7 +204,7 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 			if (ex.on) row_inv<SH, TRANS, true>(o, ex); else row_inv<SH, TRANS, false>(o, ex);
 			const int row = half ? r2 : r1;
 			if (DST == DST_U8_RGB) {
-				s_stage[grp][set][slot][plane][half][lane] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+				(*stage)[set][slot][plane][half][lane] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
 				continue;
 			}
 			if (!(row >= y0 && row < y1 && lane_out)) continue;
@@ -249,8 +246,8 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 					for (int half = 0; half < 2; half++) {
 						const int row = half ? 2 * tt - 3 : 2 * tt - 4;
 						if (!(row >= y0 && row < y1 && lane_out)) continue;
-						const uint4 c0 = s_stage[grp][set][my][0][half][lane], c1 = s_stage[grp][set][my][1][half][lane],
-						            c2 = s_stage[grp][set][my][2][half][lane];
+						const uint4 c0 = (*stage)[set][my][0][half][lane], c1 = (*stage)[set][my][1][half][lane],
+						            c2 = (*stage)[set][my][2][half][lane];
 						unsigned R[8], G[8], B[8];
 #pragma unroll
 						for (int k = 0; k < 8; k++) {  // YCoCgtoRGB<shift>, ric.cpp:93-112 (planes 0 Co, 1 Cg, 2 Y)
@@ -285,6 +282,29 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 				}
 			}
 		}
+	}
+}
+
+// Persistent CTAs with dynamic job fetch (see fwd_level_kernel).
+template <bool SH, int TRANS, int DST>
+__global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_WARPS * 32, DST == DST_U8_RGB ? 3 : 4)
+    inv_level_kernel(const __grid_constant__ InvParams P)
+{
+	constexpr bool RGB = DST == DST_U8_RGB;
+	constexpr int JOBS = RGB ? INV_RGB_GROUPS : INV_WARPS;  // jobs claimed per CTA and round
+	__shared__ uint4 s_stage_raw[RGB ? INV_RGB_GROUPS * (sizeof(RgbStage) / sizeof(uint4)) : 1];
+	RgbStage *s_stage = (RgbStage *)s_stage_raw;
+	__shared__ unsigned long long s_base;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int slot = RGB ? wib / 3 : wib, wig = RGB ? wib % 3 : 0;
+	const long long njobs = (long long)P.nstrips * (RGB ? 1 : P.nplanes) * P.nsegs * P.nimages;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) s_base = atomicAdd(P.counter, (unsigned long long)JOBS);
+		__syncthreads();
+		const long long base = (long long)s_base;
+		if (base >= njobs) break;
+		if (base + slot < njobs) inv_job<SH, TRANS, DST>(P, base + slot, s_stage + (RGB ? slot : 0), slot, wig, lane);
 	}
 }
 

@@ -286,3 +286,27 @@ def test_stream_api_chunk_callbacks():
         assert sum(k for _, k in seen2) == n
         for i in range(n):
             assert np.array_equal(dec[i], o.decode_image(signed[i * c.image_arena_bytes:(i + 1) * c.image_arena_bytes], ch, q))
+
+
+def test_contexts_are_independent_across_threads():
+    """One ric_ctx per thread (the reference's threading rule): concurrent encodes on
+    different contexts do not interfere."""
+    import threading
+    shapes = [(320, 200, 3), (250, 131, 1), (512, 256, 3), (129, 130, 1)]
+    results = {}
+
+    def work(k):
+        w, h, ch = shapes[k]
+        img = synth_image(k, w, h, ch)
+        with capi.Context(w, h, ch, 5) as c:
+            for _ in range(5):
+                results[k] = c.encode_u8(img[None], 9)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(shapes))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k, (w, h, ch) in enumerate(shapes):
+        want = oraclebind.Oracle(w, h, 5).encode_image(synth_image(k, w, h, ch), 9)
+        assert np.array_equal(results[k], want), k
