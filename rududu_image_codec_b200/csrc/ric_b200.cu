@@ -109,9 +109,9 @@ __global__ void quant_level_kernel(const __grid_constant__ QuantLevelParams P)
 	const BandRef &b = P.band[o];
 	const int nbx = b.fl_bw, nby = (b.dimy + 3) / 4;
 	const int id = blockIdx.x * blockDim.x + threadIdx.x;
-	if (id >= nbx * nby) return;
-	const int bx = id % nbx, by = id / nbx;
-	const int bw = min(4, b.dimx - 4 * bx), bh = min(4, b.dimy - 4 * by);
+	const bool have = id < nbx * nby;  // threads past the last block run the quantiser on an empty block (full-warp votes inside)
+	const int bx = have ? id % nbx : 0, by = have ? id / nbx : 0;
+	const int bw = have ? min(4, b.dimx - 4 * bx) : 0, bh = have ? min(4, b.dimy - 4 * by) : 0;
 	constexpr int ES = SH ? 2 : 4;
 	char *base = P.arena + b.off;
 	int c[16];
@@ -125,6 +125,7 @@ __global__ void quant_level_kernel(const __grid_constant__ QuantLevelParams P)
 		}
 	}
 	int nz = quant_block<SH>(c, &s_qb[o], bw, bh);
+	if (!have) return;
 	if (P.has_child && bw == 4 && bh == 4) {
 		const BandRef &ch = P.child[o];
 		const unsigned char *cf = P.flags + ch.fl_off + (2 * by) * ch.fl_bw + 2 * bx;

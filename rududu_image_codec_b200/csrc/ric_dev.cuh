@@ -315,7 +315,7 @@ __device__ __forceinline__ int quant_block(int (&c)[16], const QuantBand *qb, in
 	unsigned alive = 0;
 #pragma unroll
 	for (int k = 0; k < 16; k++) alive |= ((unsigned)(c[k] + T) > T2) ? (1u << k) : 0u;
-	if (!__any_sync(__activemask(), alive != 0)) {
+	if (!__any_sync(FULL, alive != 0)) {  // callers keep the warp converged (flush_blocks / quant_level_kernel)
 #pragma unroll
 		for (int k = 0; k < 16; k++) c[k] = 0;
 		return 0;
@@ -338,8 +338,7 @@ __device__ __forceinline__ int quant_block(int (&c)[16], const QuantBand *qb, in
 		cnt += (live && !cand) ? 1 : 0;
 		nc += cand ? 1 : 0;
 	}
-	const unsigned act = __activemask();
-	const int ncm = __reduce_max_sync(act, nc);  // largest candidate count among this warp's blocks
+	const int ncm = __reduce_max_sync(FULL, nc);  // largest candidate count among this warp's blocks
 	if (ncm > 0) {
 		int kstar = 0x7fffffff, m = 0;
 		if (ncm == 1) {

@@ -196,17 +196,20 @@ __device__ __forceinline__ void ring_get(const Ring<SH> &rg, int o, int row, int
 }
 
 // Quantise (optionally) and write block row `by` of the three bands from the staging ring.
-// One lane = one 4x4 block per band (bx = this lane's block column).
+// One lane = one 4x4 block per band (bx = this lane's block column).  Called by all 32 lanes of the
+// warp (the quantiser uses full-warp votes); lanes without a block in the band (halo lanes, columns
+// or rows beyond the band) run it on an empty block and store nothing.
 template <bool SH>
 __device__ __forceinline__ void flush_blocks(const FwdParams &P, const Ring<SH> &rg, char *arena, unsigned char *flags,
-                                          const QuantBand *qb3, int bx, int by, int lane)
+                                             const QuantBand *qb3, int bx, int by, int lane, bool lane_out)
 {
 #pragma unroll 1
 	for (int o = 0; o < 3; o++) {
 		const BandRef &b = P.band[o];
 		const int x0 = bx * 4, y0 = by * 4;
-		if (x0 >= b.dimx || y0 >= b.dimy) continue;
-		const int bw = min(4, b.dimx - x0), bh = min(4, b.dimy - y0);
+		if (y0 >= b.dimy) continue;  // warp-uniform
+		const bool have = lane_out && x0 < b.dimx;
+		const int bw = have ? min(4, b.dimx - x0) : 0, bh = min(4, b.dimy - y0);
 		int c[16];
 #pragma unroll
 		for (int r = 0; r < 4; r++) ring_get<SH>(rg, o, y0 + r, lane, c[4 * r], c[4 * r + 1], c[4 * r + 2], c[4 * r + 3]);
@@ -217,9 +220,10 @@ __device__ __forceinline__ void flush_blocks(const FwdParams &P, const Ring<SH> 
 				const unsigned char *cf = flags + ch.fl_off + (2 * by) * ch.fl_bw + 2 * bx;
 				nz += cf[0] + cf[1] + cf[ch.fl_bw] + cf[ch.fl_bw + 1];  // (odd fl_bw: the second row is not 2-byte aligned)
 			}
-			flags[b.fl_off + by * b.fl_bw + bx] = nz != 0;
+			if (have) flags[b.fl_off + by * b.fl_bw + bx] = nz != 0;
 			if (nz == 0) c[0] = -0x8000;  // INSIGNIF_BLOCK, bandcodec.cpp:113,272
 		}
+		if (!have) continue;
 		char *base = arena + b.off;
 		const int es = SH ? 2 : 4;
 		if (bw == 4) {
@@ -361,7 +365,7 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<
 		}
 		if ((jv & 3) == 3) {  // block row jv>>2 of D, H and V is complete (D/H rows sit one slot ahead in the ring)
 			const int by = jv >> 2;
-			if (by >= (y0 >> 3) && lane_out) flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane);
+			if (by >= (y0 >> 3)) flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
 		}
 		// rotate the vertical state
 #pragma unroll
