@@ -303,6 +303,8 @@ def run_ours(args):
                 tj = json.load(open(traffic_file))  # ncu dram__bytes_read+write of this kernel on this workload
                 line["roofline"]["traffic"] = tj["fwd_level0_bytes_per_launch"] * S / tj["fwd_level0_samples_per_launch"]
                 line["roofline"]["traffic_source"] = "profiles/traffic.json (ncu --set full, scaled per sample to this batch)"
+                if "limiter" in tj:
+                    line["roofline"]["limiter"] = tj["limiter"]
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:

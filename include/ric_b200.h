@@ -66,7 +66,9 @@ typedef struct {
 /* ---- context -------------------------------------------------------------------------------
  * Replaces CWavelet2D::CWavelet2D / Init (wavelet2d.cpp:38-81), CBand::Init (band.cpp:51-65) and
  * SetWeight (wavelet2d.cpp:1009-1032) for `channels` planes of up to `max_batch` images on CUDA
- * device `device`.  trans selects the lifting (cdf97, cdf53; haar is RIC_E_UNSUPPORTED on GPU). */
+ * device `device`.  trans selects the lifting: cdf97, cdf53, or haar (haar only when every level has
+ * even width and height -- the reference's Haar leaves odd trailing rows/columns undefined -- else
+ * RIC_E_UNSUPPORTED). */
 int ric_create(ric_ctx **out, int device, int width, int height, int channels, int levels,
                int level_chg, int align, int trans, int max_batch);
 int ric_destroy(ric_ctx *ctx);

@@ -53,7 +53,7 @@ public:
 	CWavelet2D(int x, int y, int level, int level_chg = 0, int Align = ALIGN, int device = 0)
 	    : DimX(x), DimY(y), levels_(level), level_chg_(level_chg), align_(Align), device_(device)
 	{
-		ctx_[0] = ctx_[1] = 0;
+		ctx_[0] = ctx_[1] = ctx_[2] = 0;
 		arena_ = 0;
 		ric_ctx *c = ctx(cdf97);
 		ric_info inf;
@@ -70,7 +70,7 @@ public:
 		for (CWavelet2D *w = pLow; w;) { CWavelet2D *n = w->pLow; w->pLow = 0; delete w; w = n; }
 		if (!pHigh) {
 			if (arena_) ric_host_free(arena_);
-			for (int i = 0; i < 2; i++)
+			for (int i = 0; i < 3; i++)
 				if (ctx_[i]) ric_destroy(ctx_[i]);
 		}
 	}
@@ -132,7 +132,7 @@ public:
 	size_t arena_bytes() const { return arena_bytes_; }
 
 private:
-	CWavelet2D(CWavelet2D *high, int x, int y) : pHigh(high), DimX(x), DimY(y) { ctx_[0] = ctx_[1] = 0; arena_ = 0; }
+	CWavelet2D(CWavelet2D *high, int x, int y) : pHigh(high), DimX(x), DimY(y) { ctx_[0] = ctx_[1] = ctx_[2] = 0; arena_ = 0; }
 
 	static void check(int rc)
 	{
@@ -144,7 +144,6 @@ private:
 	ric_ctx *ctx(trans t)
 	{
 		CWavelet2D *T = top();
-		if (t != cdf97 && t != cdf53) throw std::runtime_error("rududu_b200: only cdf97 / cdf53 run on the GPU");
 		if (!T->ctx_[t]) check(ric_create(&T->ctx_[t], T->device_, T->DimX, T->DimY, 1, T->levels_, T->level_chg_, T->align_, t, 1));
 		return T->ctx_[t];
 	}
@@ -174,7 +173,7 @@ private:
 		}
 	}
 
-	ric_ctx *ctx_[2];
+	ric_ctx *ctx_[3];
 	char *arena_;
 	size_t arena_bytes_ = 0;
 	int levels_ = 0, level_chg_ = 0, align_ = ALIGN, device_ = 0, nlev_ = 0;

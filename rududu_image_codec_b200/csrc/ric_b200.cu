@@ -69,20 +69,23 @@ typedef void (*inv_fn)(const InvParams);
 
 static fwd_fn pick_fwd(bool sh, int trans, int src)
 {
-#define RIC_F(SHV, TR_, SRC_) if (sh == SHV && trans == (TR_ == T97 ? RIC_CDF97 : RIC_CDF53) && src == SRC_) return fwd_level_kernel<SHV, TR_, SRC_>;
+#define RIC_F(SHV, TR_, SRC_) if (sh == SHV && trans == (TR_ == T97 ? RIC_CDF97 : TR_ == T53 ? RIC_CDF53 : RIC_HAAR) && src == SRC_) return fwd_level_kernel<SHV, TR_, SRC_>;
 	RIC_F(true, T97, SRC_U8_GRAY) RIC_F(true, T97, SRC_U8_RGB) RIC_F(true, T97, SRC_S16)
 	RIC_F(false, T97, SRC_S16) RIC_F(false, T97, SRC_S32)
 	RIC_F(true, T53, SRC_U8_GRAY) RIC_F(true, T53, SRC_U8_RGB) RIC_F(true, T53, SRC_S16)
 	RIC_F(false, T53, SRC_S16) RIC_F(false, T53, SRC_S32)
+	RIC_F(true, THAAR, SRC_U8_GRAY) RIC_F(true, THAAR, SRC_U8_RGB) RIC_F(true, THAAR, SRC_S16)
+	RIC_F(false, THAAR, SRC_S16) RIC_F(false, THAAR, SRC_S32)
 #undef RIC_F
 	return nullptr;
 }
 
 static inv_fn pick_inv(bool sh, int trans, int dst)
 {
-#define RIC_I(SHV, TR_, DST_) if (sh == SHV && trans == (TR_ == T97 ? RIC_CDF97 : RIC_CDF53) && dst == DST_) return inv_level_kernel<SHV, TR_, DST_>;
+#define RIC_I(SHV, TR_, DST_) if (sh == SHV && trans == (TR_ == T97 ? RIC_CDF97 : TR_ == T53 ? RIC_CDF53 : RIC_HAAR) && dst == DST_) return inv_level_kernel<SHV, TR_, DST_>;
 	RIC_I(true, T97, DST_PLANE) RIC_I(true, T97, DST_U8_GRAY) RIC_I(true, T97, DST_U8_RGB) RIC_I(false, T97, DST_PLANE)
 	RIC_I(true, T53, DST_PLANE) RIC_I(true, T53, DST_U8_GRAY) RIC_I(true, T53, DST_U8_RGB) RIC_I(false, T53, DST_PLANE)
+	RIC_I(true, THAAR, DST_PLANE) RIC_I(true, THAAR, DST_U8_GRAY) RIC_I(true, THAAR, DST_U8_RGB) RIC_I(false, THAAR, DST_PLANE)
 #undef RIC_I
 	return nullptr;
 }

@@ -10,7 +10,7 @@
 
 namespace ric {
 
-enum { T97 = 0, T53 = 1 };
+enum { T97 = 0, T53 = 1, THAAR = 2 };  // Haar: S1/S2 (U2/U1) only, pairs without neighbours; even sizes only
 
 // Strip geometry: one warp owns STRIP_W output columns and loads 8 more on each side
 // (lane 0 and lane 31 are halo lanes); every lane holds 8 consecutive columns.
@@ -43,6 +43,7 @@ template <bool SH, int TRANS>
 __device__ __forceinline__ int fS1(int x, int l, int r)
 {
 	if (TRANS == T97) { int t = TR<SH>(l + r); return TR<SH>(x - (t + (t >> 1))); }
+	if (TRANS == THAAR) return TR<SH>(x - r);  // i[0] -= i[1], wavelet2d.cpp:772
 	return TR<SH>(x - ((l + r) >> 1));
 }
 template <bool SH, int TRANS>
@@ -54,6 +55,7 @@ template <bool SH, int TRANS>
 __device__ __forceinline__ int fS2(int x, int l, int r)
 {
 	if (TRANS == T97) return TR<SH>(x - ((l + r) >> 4));
+	if (TRANS == THAAR) return TR<SH>(x + (l >> 1));  // i[1] += i[0] >> 1, wavelet2d.cpp:773
 	return TR<SH>(x + ((l + r) >> 2));
 }
 template <bool SH, int TRANS>
@@ -104,6 +106,7 @@ template <bool SH, int TRANS>
 __device__ __forceinline__ int iU2(int x, int l, int r)
 {
 	if (TRANS == T97) return x + ((l + r) >> 4);
+	if (TRANS == THAAR) return TR<SH>(x - (l >> 1));  // i[1] -= i[0] >> 1, wavelet2d.cpp:784
 	return TR<SH>(x - ((l + r) >> 2));  // 5/3: feeds the un-truncated (l + r) >> 1 of U1
 }
 template <bool SH, int TRANS>
@@ -112,6 +115,7 @@ template <bool SH, int TRANS>
 __device__ __forceinline__ int iU1(int x, int l, int r)
 {
 	if (TRANS == T97) { int t = TR<SH>(l + r); return x + (t + (t >> 1)); }
+	if (TRANS == THAAR) return TR<SH>(x + r);  // i[0] += i[1], wavelet2d.cpp:785
 	return TR<SH>(x + ((l + r) >> 1));
 }
 template <bool SH, int TRANS>

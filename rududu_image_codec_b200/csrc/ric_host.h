@@ -46,7 +46,7 @@ inline int geom_init(HostGeom &g, int w, int h, int ch, int levels, int level_ch
 	if (ch != 1 && ch != 3) return RIC_E_ARG;
 	if (levels < 1 || levels > RIC_MAX_LEVELS || level_chg < 0 || level_chg >= levels) return RIC_E_ARG;
 	if (align < 32 || (align & (align - 1))) return RIC_E_ARG;  // kernels rely on >= 32-byte rows
-	if (trans != RIC_CDF97 && trans != RIC_CDF53) return RIC_E_UNSUPPORTED;
+	if (trans != RIC_CDF97 && trans != RIC_CDF53 && trans != RIC_HAAR) return RIC_E_UNSUPPORTED;
 	g.width = w; g.height = h; g.channels = ch; g.levels = levels; g.level_chg = level_chg;
 	g.align = align; g.trans = trans;
 	int x = w, y = h, lv = levels, n = 0;
@@ -62,6 +62,9 @@ inline int geom_init(HostGeom &g, int w, int h, int ch, int levels, int level_ch
 		break;
 	}
 	if (x < 8 || y < 8) return RIC_E_ARG;  // lifting needs a few samples per line
+	if (trans == RIC_HAAR)  // the reference's Haar leaves odd trailing rows/columns unprocessed and the matching
+		for (int i = 0; i < n; i++)  // band samples uninitialised (wavelet2d.cpp:802,838): even sizes only
+			if ((g.lev_w[i] | g.lev_h[i]) & 1) return RIC_E_UNSUPPORTED;
 	g.nlev = n;
 	g.nbands = 3 * n + 1;
 	const float scale = trans == RIC_CDF97 ? 1.149604398f * 1.149604398f : 2.f;

@@ -57,5 +57,6 @@ def test_argument_validation_needs_no_gpu():
     assert L.ric_create(ctypes.byref(h), 0, 8, 8, 1, 5, 1, 32, 0, 1) == capi.E_ARG
     assert L.ric_create(ctypes.byref(h), 0, 64, 64, 2, 5, 1, 32, 0, 1) == capi.E_ARG
     assert L.ric_create(ctypes.byref(h), 0, 64, 64, 1, 5, 5, 32, 0, 1) == capi.E_ARG
-    assert L.ric_create(ctypes.byref(h), 0, 64, 64, 1, 5, 1, 32, 2, 1) == capi.E_UNSUPPORTED
+    assert L.ric_create(ctypes.byref(h), 0, 66, 64, 1, 5, 1, 32, 2, 1) == capi.E_UNSUPPORTED  # Haar, odd level width
+    assert L.ric_create(ctypes.byref(h), 0, 64, 64, 1, 5, 1, 32, 3, 1) == capi.E_UNSUPPORTED  # unknown transform
     assert L.ric_destroy(None) == 0

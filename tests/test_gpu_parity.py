@@ -180,7 +180,7 @@ def test_error_codes():
         capi.Context(8, 8)
     assert e.value.code == capi.E_ARG
     with pytest.raises(capi.RicError) as e:
-        capi.Context(64, 64, trans=capi.HAAR)
+        capi.Context(66, 64, trans=capi.HAAR)  # 33 columns at the second level
     assert e.value.code == capi.E_UNSUPPORTED
     with capi.Context(64, 64) as c:
         with pytest.raises(capi.RicError):
@@ -310,3 +310,33 @@ def test_contexts_are_independent_across_threads():
     for k, (w, h, ch) in enumerate(shapes):
         want = oraclebind.Oracle(w, h, 5).encode_image(synth_image(k, w, h, ch), 9)
         assert np.array_equal(results[k], want), k
+
+
+@pytest.mark.parametrize("w,h,levels,chg", [(512, 512, 5, 1), (320, 192, 5, 1), (64, 96, 3, 0), (640, 352, 5, 0), (1920, 1088, 5, 1)])
+def test_haar(w, h, levels, chg):
+    rng = np.random.default_rng(w + h)
+    plane = rng.integers(-32768, 32768, size=(h, w), dtype=np.int16)
+    o = oraclebind.Oracle(w, h, levels, chg, trans=2)
+    with capi.Context(w, h, 1, levels, chg, trans=capi.HAAR) as c:
+        got = c.transform(plane)
+        assert _diff(o, got, o.forward(plane)) is None
+        assert np.array_equal(c.transform_inv(got), plane)
+    # whole stage, lossless and lossy, RGB
+    img = synth_image(4, w, h, 3)
+    for q in (0, 9):
+        want = o.encode_image(img, q)
+        with capi.Context(w, h, 3, levels, chg, trans=capi.HAAR) as c:
+            got = c.encode_u8(img[None], q)
+            assert np.array_equal(got, want)
+            for p in range(3):
+                o.unfold(want[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+            dec = c.decode_u8(want, 1, q)[0]
+        assert np.array_equal(dec, o.decode_image(want, 3, q))
+        if q == 0:
+            assert np.array_equal(dec, img)
+
+
+def test_haar_odd_sizes_are_refused():
+    with pytest.raises(capi.RicError) as e:
+        capi.Context(1920, 1080, trans=capi.HAAR)  # 1080/8 = 135 is odd at level 4
+    assert e.value.code == capi.E_UNSUPPORTED

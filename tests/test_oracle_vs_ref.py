@@ -166,3 +166,21 @@ def test_quant_half_plus_entropy_half_is_codeband(w, h, ch, q):
     assert np.array_equal(ref_payload_from_arenas(o, arenas, ch), want)
     ours = oraclebind.Oracle(w, h, 5).encode_image(img, q)
     assert np.array_equal(ref_payload_from_arenas(o, ours, ch), want)
+
+
+@pytest.mark.parametrize("w,h,levels,chg", [(512, 512, 5, 1), (320, 192, 5, 1), (64, 96, 3, 0), (640, 352, 5, 0)])
+def test_haar_even_sizes(w, h, levels, chg):
+    """Haar (src/lib/wavelet2d.cpp:766-855) where it is well defined: every level has even width and
+    height (odd trailing rows/columns are left unprocessed by the reference)."""
+    rng = np.random.default_rng(w + h)
+    plane = rng.integers(-32768, 32768, size=(h, w), dtype=np.int16)
+    o = oraclebind.Oracle(w, h, levels, chg, trans=2)
+    r = refbind.RefWavelet(w, h, levels, chg, 2)
+    r.transform(plane.copy())
+    a = o.forward(plane)
+    assert _bands_equal(o, a, ref_plane_arena(o, r)) is None
+    for i in range(o.nbands):
+        r.set_band(i, o.band_view(a, i))
+    assert np.array_equal(o.inverse(a), r.transform_inv())
+    assert np.array_equal(o.inverse(a), plane)
+    r.close()
