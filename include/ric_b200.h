@@ -140,6 +140,13 @@ int ric_tsuq(ric_ctx *ctx, int Quant, float thres, void *arena, unsigned *count)
 int ric_tsuqi(ric_ctx *ctx, int Quant, void *arena);
 int ric_transform_inv(ric_ctx *ctx, const void *arena, int16_t *plane, int stride);
 
+/* ---- .ric container header (src/ric/ric.cpp:114-121,135,150-154,187-200) --------------------------
+ * 9 bytes: "RUD2", u16 LE width, u16 LE height, one byte Quant:5 | Color:1 << 5 | Trans:2 << 6.
+ * The payload that follows is the entropy coder's buffer from offset 2 (ric.cpp:176). */
+#define RIC_HEADER_BYTES 9
+int ric_header_write(uint8_t *out, int width, int height, int q, int color, int trans);
+int ric_header_parse(const uint8_t *in, int *width, int *height, int *q, int *color, int *trans);
+
 /* pinned host memory helpers (arenas handed to host entropy threads should be pinned) */
 int ric_host_alloc(void **p, size_t bytes);
 int ric_host_free(void *p);

@@ -22,7 +22,7 @@ EXPORTS = [
     "ric_plane_quant", "ric_encode_u8", "ric_decode_u8", "ric_encode_u8_device", "ric_decode_u8_device",
     "ric_last_launch_count", "ric_transform", "ric_quant", "ric_tsuq", "ric_tsuqi", "ric_transform_inv",
     "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times",
-    "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync",
+    "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync", "ric_header_write", "ric_header_parse",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
         L.ric_encode_u8_stream.argtypes = [vp, vp, i, i, vp, CHUNK_FN, vp]
         L.ric_decode_u8_stream.argtypes = [vp, vp, i, i, vp, CHUNK_FN, vp]
         L.ric_sync.argtypes = [vp]
+        L.ric_header_write.argtypes = [vp, i, i, i, i, i]
+        L.ric_header_parse.argtypes = [vp] + [C.POINTER(i)] * 5
         L.ric_get_level_times.argtypes = [vp, i, C.POINTER(C.c_float), i]
         _lib = L
     return _lib
@@ -99,6 +101,19 @@ def plane_quant(q, channels, plane):
     a, b = C.c_int(), C.c_int()
     _check(lib().ric_plane_quant(q, channels, plane, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+def header_write(width, height, q, color, trans):
+    buf = (C.c_uint8 * 9)()
+    _check(lib().ric_header_write(buf, width, height, q, color, trans))
+    return bytes(buf)
+
+
+def header_parse(data):
+    buf = (C.c_uint8 * 9).from_buffer_copy(bytes(data[:9]))
+    v = [C.c_int() for _ in range(5)]
+    _check(lib().ric_header_parse(buf, *[C.byref(x) for x in v]))
+    return tuple(x.value for x in v)
 
 
 def _ptr(a):

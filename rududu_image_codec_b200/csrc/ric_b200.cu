@@ -357,6 +357,29 @@ int ric_get_level_times(ric_ctx *c, int direction, float *ms, int cap)
 	return n;
 }
 
+int ric_header_write(uint8_t *out, int width, int height, int q, int color, int trans)
+{
+	if (!out || width < 1 || width > 65535 || height < 1 || height > 65535 || q < 0 || q > 31 || (color & ~1) || trans < 0 || trans > 2)
+		return set_err(RIC_E_ARG, "ric_header_write: bad argument");
+	out[0] = 'R'; out[1] = 'U'; out[2] = 'D'; out[3] = '2';
+	out[4] = (uint8_t)(width & 0xFF); out[5] = (uint8_t)(width >> 8);
+	out[6] = (uint8_t)(height & 0xFF); out[7] = (uint8_t)(height >> 8);
+	out[8] = (uint8_t)(q | color << 5 | trans << 6);
+	return RIC_OK;
+}
+
+int ric_header_parse(const uint8_t *in, int *width, int *height, int *q, int *color, int *trans)
+{
+	if (!in || !width || !height || !q || !color || !trans) return set_err(RIC_E_ARG, "ric_header_parse: null");
+	if (in[0] != 'R' || in[1] != 'U' || in[2] != 'D' || in[3] != '2') return set_err(RIC_E_ARG, "ric_header_parse: bad magic (ric.cpp:189-190)");
+	*width = in[4] | in[5] << 8;
+	*height = in[6] | in[7] << 8;
+	*q = in[8] & 31;
+	*color = (in[8] >> 5) & 1;
+	*trans = in[8] >> 6;
+	return RIC_OK;
+}
+
 int ric_host_alloc(void **p, size_t bytes)
 {
 	if (!p) return set_err(RIC_E_ARG, "ric_host_alloc: null");

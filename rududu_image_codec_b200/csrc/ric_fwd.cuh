@@ -373,26 +373,26 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<
 	}
 }
 
-// Persistent CTAs: each CTA repeatedly claims the next FWD_WARPS consecutive jobs (one per warp) from a
-// global counter, so a launch has no wave-quantisation tail beyond one job; consecutive jobs (the
-// planes of one strip) stay in one CTA and keep sharing their pixel loads through L1.
+// Persistent warps: every warp repeatedly claims the next job from a global counter, so a launch has
+// no wave-quantisation tail beyond one job and the heavier luma jobs (more quantiser work) do not
+// hold back the chroma warps of their CTA.  Consecutive job ids are the planes of one strip: they
+// are claimed at about the same time, so their shared pixel loads still meet in L1/L2.
 template <bool SH, int TRANS, int SRC>
 __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const __grid_constant__ FwdParams P)
 {
 	constexpr int FWD_WARPS = fwd_warps(SH);
 	__shared__ QuantBand s_qb[2][3];
 	__shared__ Ring<SH> s_ring[FWD_WARPS];
-	__shared__ unsigned long long s_base;
 	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
+	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const long long njobs = (long long)P.nstrips * P.nplanes * P.nsegs * P.nimages;
 	for (;;) {
-		__syncthreads();
-		if (threadIdx.x == 0) s_base = atomicAdd(P.counter, (unsigned long long)FWD_WARPS);
-		__syncthreads();
-		const long long base = (long long)s_base;
-		if (base >= njobs) break;
-		if (base + wib < njobs) fwd_job<SH, TRANS, SRC>(P, base + wib, s_ring[wib], s_qb, lane);
+		unsigned long long job = 0;
+		if (lane == 0) job = atomicAdd(P.counter, 1ull);
+		job = __shfl_sync(FULL, job, 0);
+		if ((long long)job >= njobs) break;
+		fwd_job<SH, TRANS, SRC>(P, (long long)job, s_ring[wib], s_qb, lane);
 	}
 }
 

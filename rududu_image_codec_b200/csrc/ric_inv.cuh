@@ -285,26 +285,32 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 	}
 }
 
-// Persistent CTAs with dynamic job fetch (see fwd_level_kernel).
+// Persistent warps with dynamic job fetch (see fwd_level_kernel); for RGB output the three warps of a
+// group claim one job together (broadcast through shared memory under the group's named barrier).
 template <bool SH, int TRANS, int DST>
 __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_WARPS * 32, DST == DST_U8_RGB ? 3 : 4)
     inv_level_kernel(const __grid_constant__ InvParams P)
 {
 	constexpr bool RGB = DST == DST_U8_RGB;
-	constexpr int JOBS = RGB ? INV_RGB_GROUPS : INV_WARPS;  // jobs claimed per CTA and round
 	__shared__ uint4 s_stage_raw[RGB ? INV_RGB_GROUPS * (sizeof(RgbStage) / sizeof(uint4)) : 1];
+	__shared__ unsigned long long s_job[RGB ? INV_RGB_GROUPS : 1];
 	RgbStage *s_stage = (RgbStage *)s_stage_raw;
-	__shared__ unsigned long long s_base;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	const int slot = RGB ? wib / 3 : wib, wig = RGB ? wib % 3 : 0;
+	const int grp = RGB ? wib / 3 : 0, wig = RGB ? wib % 3 : 0;
 	const long long njobs = (long long)P.nstrips * (RGB ? 1 : P.nplanes) * P.nsegs * P.nimages;
 	for (;;) {
-		__syncthreads();
-		if (threadIdx.x == 0) s_base = atomicAdd(P.counter, (unsigned long long)JOBS);
-		__syncthreads();
-		const long long base = (long long)s_base;
-		if (base >= njobs) break;
-		if (base + slot < njobs) inv_job<SH, TRANS, DST>(P, base + slot, s_stage + (RGB ? slot : 0), slot, wig, lane);
+		unsigned long long job = 0;
+		if (RGB) {
+			asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory");  // everybody has read the previous job id
+			if (wig == 0 && lane == 0) s_job[grp] = atomicAdd(P.counter, 1ull);
+			asm volatile("bar.sync %0, 96;" ::"r"(grp + 1) : "memory");
+			job = s_job[grp];
+		} else {
+			if (lane == 0) job = atomicAdd(P.counter, 1ull);
+			job = __shfl_sync(FULL, job, 0);
+		}
+		if ((long long)job >= njobs) break;
+		inv_job<SH, TRANS, DST>(P, (long long)job, s_stage + grp, grp, wig, lane);
 	}
 }
 

@@ -60,3 +60,15 @@ def test_argument_validation_needs_no_gpu():
     assert L.ric_create(ctypes.byref(h), 0, 66, 64, 1, 5, 1, 32, 2, 1) == capi.E_UNSUPPORTED  # Haar, odd level width
     assert L.ric_create(ctypes.byref(h), 0, 64, 64, 1, 5, 1, 32, 3, 1) == capi.E_UNSUPPORTED  # unknown transform
     assert L.ric_destroy(None) == 0
+
+
+def test_ric_container_header():
+    """"RUD2", u16 LE width, u16 LE height, Quant:5 | Color<<5 | Trans<<6 (src/ric/ric.cpp:114-121,150-154)."""
+    assert capi.header_write(3840, 2160, 9, 1, 0) == b"RUD2" + bytes([0x00, 0x0F, 0x70, 0x08, 9 | 1 << 5])
+    assert capi.header_write(512, 512, 0, 0, 1) == b"RUD2" + bytes([0x00, 0x02, 0x00, 0x02, 1 << 6])
+    for args in [(65535, 1, 31, 1, 2), (16, 65535, 0, 0, 0), (1920, 1080, 20, 1, 1)]:
+        assert capi.header_parse(capi.header_write(*args)) == args
+    with pytest.raises(capi.RicError):
+        capi.header_parse(b"RUD1" + bytes(5))
+    with pytest.raises(capi.RicError):
+        capi.header_write(70000, 10, 9, 1, 0)
