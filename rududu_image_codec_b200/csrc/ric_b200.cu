@@ -213,8 +213,10 @@ static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_imag
 		const long long nseg = (h + seg - 1) / seg, rem = h - (nseg - 1) * seg;  // last segment may be short
 		const long long it = (seg < h ? seg : ((h + 7) & ~7)) / 2 + 4, it_last = ((rem + 7) & ~7) / 2 + 4;
 		const long long cols = nstrips * planes_images;          // independent columns of segments
-		const long long jobs = cols * nseg, work = cols * ((nseg - 1) * it + it_last);
-		const long long cost = jobs <= slots ? 2 * it : 2 * ((work + slots - 1) / slots) + it;  // (x2: half-job tail)
+		const long long work = cols * ((nseg - 1) * it + it_last);
+		// jobs differ in weight (luma blocks cost more quantiser work than chroma), so even a single wave
+		// benefits from several jobs per slot: charge a full job as the tail
+		const long long cost = (work + slots - 1) / slots + it;
 		if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = seg; }
 	}
 	return best;
