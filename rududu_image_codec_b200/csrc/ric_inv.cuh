@@ -105,10 +105,15 @@ __device__ __forceinline__ void load_in(RawIn<SH> &in, const InvParams &P, const
 	}
 }
 
-// unpack + dequantise (TSUQi: pBand[n] *= Quant, truncating store) into interleaved even/odd rows
-template <bool SH>
-__device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &P, int plane, int (&xe)[8], int (&xo)[8])
+// unpack + dequantise (TSUQi: pBand[n] *= Quant, truncating store) into interleaved even/odd rows.
+// 9/7: the product's own truncation is deferred -- every first use of these rows is a truncating one
+// (the (C)(l + r) temporary of U4, the C-typed result of U4 / U3, or iU4_last which truncates its
+// operand) -- 5/3 and Haar feed them straight into a shift and truncate here.
+template <bool SH, int TRANS>
+__device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &P, int qd, int qh, int qv, int ql,
+                                          int (&xe)[8], int (&xo)[8])
 {
+	constexpr bool S = SH && TRANS != T97;
 	int d[4], hh[4], v[4], l[4];
 	unpack4<SH>(in.d, d);
 	unpack4<SH>(in.h, hh);
@@ -119,14 +124,12 @@ __device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &
 		l[0] = (int)(short)(in.l.x & 0xFFFF); l[1] = in.l.x >> 16;
 		l[2] = (int)(short)(in.l.y & 0xFFFF); l[3] = in.l.y >> 16;
 	}
-	const int qd = P.dq[plane][0], qh = P.dq[plane][1], qv = P.dq[plane][2];
-	const int ql = P.llsrc == LLSRC_BAND ? P.dq[plane][3] : 1;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
-		xe[2 * k] = TR<SH>(d[k] * qd);
-		xe[2 * k + 1] = TR<SH>(hh[k] * qh);
-		xo[2 * k] = TR<SH>(v[k] * qv);
-		xo[2 * k + 1] = TR<SH>(l[k] * ql);  // also the (C) narrowing of an int LL, wavelet2d.cpp:971-980
+		xe[2 * k] = TR<S>(d[k] * qd);
+		xe[2 * k + 1] = TR<S>(hh[k] * qh);
+		xo[2 * k] = TR<S>(v[k] * qv);
+		xo[2 * k + 1] = TR<S>(l[k] * ql);  // also the (C) narrowing of an int LL, wavelet2d.cpp:971-980
 	}
 }
 
@@ -170,13 +173,15 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 	for (int k = 0; k < 8; k++) se0[k] = so4[k] = se3[k] = so2[k] = 0;
 
 	const int t_begin = max((y0 >> 1) - 2, 0), t_last = (y1 + 3) >> 1;
+	const int qd = P.dq[plane][0], qh = P.dq[plane][1], qv = P.dq[plane][2];
+	const int ql = P.llsrc == LLSRC_BAND ? P.dq[plane][3] : 1;
 	RawIn<SH> in;
 	load_in<SH>(in, P, arena, llp, t_begin, bc, col_ok);
 
 #pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
 		int xe[8], xo[8];
-		unpack_in<SH>(in, P, plane, xe, xo);
+		unpack_in<SH, TRANS>(in, P, qd, qh, qv, ql, xe, xo);
 		load_in<SH>(in, P, arena, llp, t + 1, bc, col_ok);  // prefetch
 
 		const int r4 = 2 * t - 1, r3 = 2 * t - 2, r2 = 2 * t - 3, r1 = 2 * t - 4;
