@@ -340,3 +340,55 @@ def test_haar_odd_sizes_are_refused():
     with pytest.raises(capi.RicError) as e:
         capi.Context(1920, 1080, trans=capi.HAAR)  # 1080/8 = 135 is odd at level 4
     assert e.value.code == capi.E_UNSUPPORTED
+
+
+def _adversarial_images(w, h, ch, rng):
+    yy, xx = np.mgrid[0:h, 0:w]
+    chk = (((xx + yy) & 1) * 255).astype(np.uint8)
+    yield "uniform noise", rng.integers(0, 256, size=(ch, h, w), dtype=np.uint8)
+    yield "checkerboard", np.stack([chk if c != 1 else 255 - chk for c in range(ch)])
+    yield "column stripes", np.stack([((xx & 1) * 255).astype(np.uint8)] * ch)
+    yield "row stripes 2", np.stack([(((yy >> 1) & 1) * 255).astype(np.uint8) if c == 0 else rng.integers(0, 2, size=(h, w), dtype=np.uint8) * 255
+                                     for c in range(ch)])
+    yield "saturated", np.full((ch, h, w), 255, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("q", [0, 1, 9, 31])
+def test_adversarial_pixels(ch, q):
+    """Worst-case 8-bit inputs (maximum-amplitude alternation): the deepest levels really wrap around
+    in int16 here, and the level-0 row pass runs without truncation (proved bound) -- both must match
+    the reference arithmetic bit for bit."""
+    w, h = 496, 264
+    trans = 1 if q == 0 else 0
+    rng = np.random.default_rng(q * 10 + ch)
+    o = oraclebind.Oracle(w, h, 5, trans=trans)
+    with capi.Context(w, h, ch, 5, trans=trans) as c:
+        for name, img in _adversarial_images(w, h, ch, rng):
+            img = np.ascontiguousarray(img)
+            want = o.encode_image(img, q)
+            got = c.encode_u8(img[None], q)
+            assert _diff(o, got, want, ch) is None, name
+            for p in range(ch):
+                o.unfold(want[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+            assert np.array_equal(c.decode_u8(want, 1, q)[0], o.decode_image(want, ch, q)), name
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("q,trans", [(9, 0), (31, 0), (0, 1), (9, 2), (0, 0)])
+def test_decode_stage_full_range_arenas(ch, q, trans):
+    """Decode stage on arbitrary full-range coefficient arenas (what a corrupt or hostile bitstream
+    could produce): dequantisation products, lifting and the colour transform all wrap as the
+    reference's short arithmetic does."""
+    w, h = 320, 192
+    rng = np.random.default_rng(100 * q + trans + ch)
+    o = oraclebind.Oracle(w, h, 5, trans=trans)
+    arenas = np.zeros(ch * o.arena_bytes, dtype=np.uint8)
+    for p in range(ch):
+        for i in range(o.nbands):
+            f = o.info(i)
+            lo, hi = (-2 ** 31, 2 ** 31) if f["is_int"] else (-32768, 32768)
+            o.band_view(arenas, i, p)[:, :f["dimx"]] = rng.integers(lo, hi, size=(f["dimy"], f["dimx"]))
+    with capi.Context(w, h, ch, 5, trans=trans) as c:
+        got = c.decode_u8(arenas, 1, q)[0]
+    assert np.array_equal(got, o.decode_image(arenas, ch, q))
