@@ -243,9 +243,157 @@ __device__ __forceinline__ void flush_blocks(const FwdParams &P, const Ring<SH> 
 	}
 }
 
+// ---- short levels: the same flush on PACKED rows ---------------------------------------------------
+// The block never exists as 16 registers: the element-wise passes run as rolled loops over the four
+// ring rows (4 packed int16 each), write their results back into the ring in place and park the
+// candidate keys in a second lane-private shared-memory array; only the 16 keys are pulled into
+// registers for the sort.  Same arithmetic as quant_block (ric_dev.cuh), a quarter of the code:
+// the loop body of the kernel has to stay inside the instruction cache.
+typedef uint4 KeyRows[4][32];
+
+__device__ __forceinline__ int s16lo(unsigned w) { return (int)(short)(w & 0xFFFF); }
+__device__ __forceinline__ int s16hi(unsigned w) { return (int)w >> 16; }
+
+__device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<true> &rg, KeyRows &keys, char *arena,
+                                                    unsigned char *flags, const QuantBand *qb3, int bx, int by, int lane,
+                                                    bool lane_out)
+{
+#pragma unroll 1
+	for (int o = 0; o < 3; o++) {
+		const BandRef &b = P.band[o];
+		const int x0 = bx * 4, y0 = by * 4;
+		if (y0 >= b.dimy) continue;  // warp-uniform
+		const bool have = lane_out && x0 < b.dimx;
+		const int bw = have ? min(4, b.dimx - x0) : 0, bh = min(4, b.dimy - y0);
+		bool mark = false;
+		if (P.quant) {
+			const QuantBand *qb = qb3 + o;
+			const bool full = bw == 4 && bh == 4;
+			const int T = full ? qb->T : qb->Te;
+			const unsigned T2 = (unsigned)(2 * T);
+			int cnt = 0;
+			// pass 1: anything outside the dead zone in this warp's blocks?  (regular thresholds: packed min/max trees)
+			bool any_alive = have;
+			if (qb->fast && full) {
+				const uint2 r0 = rg.v[o][(y0 + 0) & (RING_ROWS - 1)][lane], r1 = rg.v[o][(y0 + 1) & (RING_ROWS - 1)][lane],
+				            r2 = rg.v[o][(y0 + 2) & (RING_ROWS - 1)][lane], r3 = rg.v[o][(y0 + 3) & (RING_ROWS - 1)][lane];
+				const unsigned mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(r0.x, r0.y, r1.x), __vimax3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
+				const unsigned mn = __vmins2(__vimin3_s16x2(__vimin3_s16x2(r0.x, r0.y, r1.x), __vimin3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
+				any_alive = max(s16lo(mx), s16hi(mx)) > T || min(s16lo(mn), s16hi(mn)) < -T;
+			}
+			if (__any_sync(FULL, any_alive)) {
+				// pass 2: fold, split into sure non-zeros (quantised now) and rank candidates (tsuqBlock :166-186)
+				const int iQ = qb->iQ;
+				const unsigned uthr0 = full ? (unsigned)(qb->thr[0] & 0xFFFF) : 0u;  // partial blocks have no candidates
+				int nc = 0;
+#pragma unroll 1
+				for (int r = 0; r < 4; r++) {
+					uint2 &row = rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane];
+					const uint2 wv = row;
+					const int v[4] = {s16lo(wv.x), s16hi(wv.x), s16lo(wv.y), s16hi(wv.y)};
+					int out[4], key[4];
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						const bool live = j < bw && r < bh && (unsigned)(v[j] + T) > T2;
+						const int sgn = (int)((unsigned)v[j] >> 31);
+						const unsigned uf = (unsigned)(2 * abs(v[j]) + sgn) & 0xFFFFu;  // s2u_ (utils.h:95-99), C-typed
+						const bool cand = live && uf < uthr0;
+						const int qq = ((int)(uf >> 1) * iQ + (1 << 15)) >> 16;          // int arithmetic as in the reference (:172)
+						out[j] = !live ? 0 : cand ? (2 | sgn) : ((qq << 1) | sgn);
+						key[j] = cand ? (int)(uf << 4) | (15 - 4 * r - j) : 0;
+						cnt += (live && !cand) ? 1 : 0;
+						nc += cand ? 1 : 0;
+					}
+					row = make_uint2((unsigned)(out[0] & 0xFFFF) | ((unsigned)out[1] << 16), (unsigned)(out[2] & 0xFFFF) | ((unsigned)out[3] << 16));
+					keys[r][lane] = make_uint4((unsigned)key[0], (unsigned)key[1], (unsigned)key[2], (unsigned)key[3]);
+				}
+				const int ncm = __reduce_max_sync(FULL, nc);  // largest candidate count among this warp's blocks
+				if (ncm > 0) {
+					int s[16];
+#pragma unroll
+					for (int r = 0; r < 4; r++) {
+						const uint4 kk = keys[r][lane];
+						s[4 * r] = (int)kk.x; s[4 * r + 1] = (int)kk.y; s[4 * r + 2] = (int)kk.z; s[4 * r + 3] = (int)kk.w;
+					}
+					int kstar = 0x7fffffff, m = 0;
+					if (ncm == 1) {  // at most one candidate per block: rank 0, survives iff f >= thr[cnt]
+						int s0 = 0;
+#pragma unroll
+						for (int k = 0; k < 16; k++) s0 = max(s0, s[k]);
+						bool pass;
+						if (qb->fast) pass = s0 >= qb->kthr[cnt];
+						else pass = s0 != 0 && !((int)(short)(s0 >> 4) < qb->thr[cnt & 15]);
+						if (pass && s0 != 0) { kstar = s0; m = 1; }
+					} else {
+						sort16_desc(s);
+						if (qb->fast) {
+							const int *kt = qb->kthr + cnt;
+#pragma unroll
+							for (int i = 0; i < 16; i++) {
+								if ((i & 3) == 0 && i >= ncm) break;  // warp-uniform
+								const bool pass = s[i] >= kt[i];
+								kstar = pass ? s[i] : kstar;
+								m = pass ? i + 1 : m;
+							}
+						} else {
+#pragma unroll
+							for (int i = 0; i < 16; i++) {
+								if (s[i] != 0) {
+									const int fs = (int)(short)(s[i] >> 4);  // signed C compare, :191
+									if (!(fs < qb->thr[(cnt + i) & 15])) { kstar = s[i]; m = i + 1; }
+								}
+							}
+						}
+					}
+					// drop the candidates ranked below the last survivor (:191-192)
+					const unsigned lim = (unsigned)(kstar - 1);
+#pragma unroll 1
+					for (int r = 0; r < 4; r++) {
+						const uint4 kk = keys[r][lane];
+						uint2 &row = rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane];
+						uint2 wv = row;
+						const unsigned m0 = (kk.x - 1u < lim) ? 0xFFFF0000u : 0xFFFFFFFFu, m1 = (kk.y - 1u < lim) ? 0x0000FFFFu : 0xFFFFFFFFu;
+						const unsigned m2 = (kk.z - 1u < lim) ? 0xFFFF0000u : 0xFFFFFFFFu, m3 = (kk.w - 1u < lim) ? 0x0000FFFFu : 0xFFFFFFFFu;
+						wv.x &= m0 & m1;
+						wv.y &= m2 & m3;
+						row = wv;
+					}
+					cnt += m;
+				}
+			} else {
+#pragma unroll
+				for (int r = 0; r < 4; r++) rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane] = make_uint2(0u, 0u);
+			}
+			int nz = cnt;
+			if (P.has_child && bw == 4 && bh == 4) {  // buildTree :267-270: add the four child blocks
+				const BandRef &ch = P.child[o];
+				const unsigned char *cf = flags + ch.fl_off + (2 * by) * ch.fl_bw + 2 * bx;
+				nz += cf[0] + cf[1] + cf[ch.fl_bw] + cf[ch.fl_bw + 1];  // (odd fl_bw: the second row is not 2-byte aligned)
+			}
+			if (have) flags[b.fl_off + by * b.fl_bw + bx] = nz != 0;
+			mark = nz == 0;  // INSIGNIF_BLOCK in the block's first sample, bandcodec.cpp:113,272
+		}
+		if (!have) continue;
+		char *base = arena + b.off;
+#pragma unroll 1
+		for (int r = 0; r < bh; r++) {
+			uint2 wv = rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane];
+			if (r == 0 && mark) wv.x = (wv.x & 0xFFFF0000u) | 0x8000u;
+			char *rowp = base + (long long)(y0 + r) * b.stride * 2 + 2 * (long long)x0;
+			if (bw == 4) *(uint2 *)rowp = wv;
+			else {
+				if (bw > 0) ((short *)rowp)[0] = (short)(wv.x & 0xFFFF);
+				if (bw > 1) ((short *)rowp)[1] = (short)(wv.x >> 16);
+				if (bw > 2) ((short *)rowp)[2] = (short)(wv.y & 0xFFFF);
+			}
+		}
+	}
+}
+
 // One job = one (image, plane, row segment, strip); see the header comment.
 template <bool SH, int TRANS, int SRC>
-__device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<SH> &rg, const QuantBand (&s_qb)[2][3], int lane)
+__device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<SH> &rg, KeyRows &keys,
+                                        const QuantBand (&s_qb)[2][3], int lane)
 {
 	// plane fastest: the planes of one RGB strip share their u8 loads through L1
 	const int plane = (int)(job % P.nplanes); job /= P.nplanes;
@@ -365,7 +513,10 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<
 		}
 		if ((jv & 3) == 3) {  // block row jv>>2 of D, H and V is complete (D/H rows sit one slot ahead in the ring)
 			const int by = jv >> 2;
-			if (by >= (y0 >> 3)) flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
+			if (by >= (y0 >> 3)) {
+				if constexpr (SH) flush_blocks_packed(P, rg, keys, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
+				else flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
+			}
 		}
 		// rotate the vertical state
 #pragma unroll
@@ -383,6 +534,7 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 	constexpr int FWD_WARPS = fwd_warps(SH);
 	__shared__ QuantBand s_qb[2][3];
 	__shared__ Ring<SH> s_ring[FWD_WARPS];
+	__shared__ KeyRows s_keys[SH ? FWD_WARPS : 1];
 	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -392,7 +544,7 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 		if (lane == 0) job = atomicAdd(P.counter, 1ull);
 		job = __shfl_sync(FULL, job, 0);
 		if ((long long)job >= njobs) break;
-		fwd_job<SH, TRANS, SRC>(P, (long long)job, s_ring[wib], s_qb, lane);
+		fwd_job<SH, TRANS, SRC>(P, (long long)job, s_ring[wib], s_keys[SH ? wib : 0], s_qb, lane);
 	}
 }
 
