@@ -441,33 +441,27 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<
 	for (int k = 0; k < 8; k++) so1[k] = se1[k] = so2[k] = se3[k] = 0;
 
 	const int t_begin = (y0 >> 1) - 2, t_last = (y1r >> 1) + 1;
-	RawRow<SRC> raw;
+	RawRow<SRC> rawE, rawO;
 	{
-		const int r0 = 2 * t_begin;
-		load_raw<SRC>(raw, src, (long long)r0 * P.src_pitch, cb, col_ok && r0 >= 0 && r0 < h, P.src_plane_stride, plane);
+		const int re = 2 * t_begin, ro = re + 1;
+		load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
+		load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 	}
-	int ne[8];
-#pragma unroll
-	for (int k = 0; k < 8; k++) ne[k] = 0;
 
-	// One source row per iteration (conversion + horizontal lifting share one copy of the code for
-	// even and odd rows: the loop body must stay inside the instruction cache); the vertical
-	// pipeline advances on every odd row.
+	// Two source rows per iteration: their conversions and horizontal passes are independent
+	// instruction streams that the scheduler interleaves.
 #pragma unroll 1
-	for (int r = 2 * t_begin; r <= 2 * t_last + 1; r++) {
-		int no[8];
-		convert_raw<SRC>(raw, no, plane, P.shift);
-		{  // prefetch the next row
-			const int rn = r + 1;
-			load_raw<SRC>(raw, src, (long long)rn * P.src_pitch, cb, col_ok && rn >= 0 && rn < h, P.src_plane_stride, plane);
+	for (int t = t_begin; t <= t_last; t++) {
+		int ne[8], no[8];
+		convert_raw<SRC>(rawE, ne, plane, P.shift);
+		convert_raw<SRC>(rawO, no, plane, P.shift);
+		{  // prefetch the next row pair
+			const int re = 2 * t + 2, ro = re + 1;
+			load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
+			load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 		}
-		if (ex.on) row_fwd<SH, TRANS, NT, true>(no, ex); else row_fwd<SH, TRANS, NT, false>(no, ex);
-		if (!(r & 1)) {
-#pragma unroll
-			for (int k = 0; k < 8; k++) ne[k] = no[k];
-			continue;
-		}
-		const int t = r >> 1;
+		if (ex.on) { row_fwd<SH, TRANS, NT, true>(ne, ex); row_fwd<SH, TRANS, NT, true>(no, ex); }
+		else { row_fwd<SH, TRANS, NT, false>(ne, ex); row_fwd<SH, TRANS, NT, false>(no, ex); }
 
 		const int r1 = 2 * t, r2 = 2 * t - 1, r3 = 2 * t - 2, r4 = 2 * t - 3;
 		// rows r4-1 .. r1+1 are touched; edge formulas if that range meets row 0 or row h-1
