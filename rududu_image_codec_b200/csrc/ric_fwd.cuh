@@ -274,7 +274,7 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<tru
 			int cnt = 0;
 			// pass 1: anything outside the dead zone in this warp's blocks?  (regular thresholds: packed min/max trees)
 			bool any_alive = have;
-			if (qb->fast && full) {
+			if (__builtin_expect(qb->fast && full, 1)) {
 				const uint2 r0 = rg.v[o][(y0 + 0) & (RING_ROWS - 1)][lane], r1 = rg.v[o][(y0 + 1) & (RING_ROWS - 1)][lane],
 				            r2 = rg.v[o][(y0 + 2) & (RING_ROWS - 1)][lane], r3 = rg.v[o][(y0 + 3) & (RING_ROWS - 1)][lane];
 				const unsigned mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(r0.x, r0.y, r1.x), __vimax3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
@@ -326,7 +326,7 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<tru
 						if (pass && s0 != 0) { kstar = s0; m = 1; }
 					} else {
 						sort16_desc(s);
-						if (qb->fast) {
+						if (__builtin_expect(qb->fast, 1)) {
 							const int *kt = qb->kthr + cnt;
 #pragma unroll
 							for (int i = 0; i < 16; i++) {
@@ -466,7 +466,7 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<
 		const int r1 = 2 * t, r2 = 2 * t - 1, r3 = 2 * t - 2, r4 = 2 * t - 3;
 		// rows r4-1 .. r1+1 are touched; edge formulas if that range meets row 0 or row h-1
 		const bool edge_y = (r4 - 1 <= 0) || (r1 + 1 >= h - 1);
-		if (edge_y) {
+		if (__builtin_expect(edge_y, 0)) {
 			if (r1 >= 0 && r1 < h) vS1<SH, TRANS, true>(ne, so1, no, r1 == 0, r1 == h - 1);
 			if (r2 >= 0 && r2 < h) vS2<SH, TRANS, true>(so1, se1, ne, false, r2 == h - 1);
 			if (r3 >= 0 && r3 < h) vS3<SH, TRANS, true>(se1, so2, so1, r3 == 0, r3 == h - 1);
