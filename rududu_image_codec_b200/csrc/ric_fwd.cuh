@@ -115,28 +115,21 @@ __device__ __forceinline__ void convert_raw(const RawRow<SRC> &raw, int (&v)[8],
 #pragma unroll
 		for (int k = 0; k < 8; k++) v[k] = (byte_of(raw.r[0], raw.r[1], k) - 128) << sh;  // ric.cpp:144 / :147
 	} else if (SRC == SRC_U8_RGB) {
-		// RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y)
-		if (plane == 0) {
-			const int sh = shift ? 3 : 0;
+		// RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y).  The three planes share one copy of
+		// the lifting chain Co -> t -> Cg -> Y; each warp stops where its plane is reached (warp-uniform).
 #pragma unroll
-			for (int k = 0; k < 8; k++) v[k] = (byte_of(raw.r[0], raw.r[1], k) - byte_of(raw.r[4], raw.r[5], k)) << sh;
-		} else if (plane == 1) {
-			const int sh = shift ? 3 : 0;
+		for (int k = 0; k < 8; k++) v[k] = byte_of(raw.r[0], raw.r[1], k) - byte_of(raw.r[4], raw.r[5], k);  // Co = R - B
+		if (plane > 0) {
 #pragma unroll
 			for (int k = 0; k < 8; k++) {
-				int R = byte_of(raw.r[0], raw.r[1], k), G = byte_of(raw.r[2], raw.r[3], k), B = byte_of(raw.r[4], raw.r[5], k);
-				int t = B + ((R - B) >> 1);
-				v[k] = (G - t) << sh;
-			}
-		} else {
-			const int sh = shift ? 4 : 0;
-#pragma unroll
-			for (int k = 0; k < 8; k++) {
-				int R = byte_of(raw.r[0], raw.r[1], k), G = byte_of(raw.r[2], raw.r[3], k), B = byte_of(raw.r[4], raw.r[5], k);
-				int t = B + ((R - B) >> 1);
-				v[k] = (t + (((G - t) >> 1) - 128)) << sh;
+				const int t = byte_of(raw.r[4], raw.r[5], k) + (v[k] >> 1);   // t = B + (Co >> 1)
+				const int cg = byte_of(raw.r[2], raw.r[3], k) - t;             // Cg = G - t
+				v[k] = plane == 2 ? t + ((cg >> 1) - 128) : cg;                // Y = t + (Cg >> 1) - 128
 			}
 		}
+		const int sh = shift ? (plane == 2 ? 4 : 3) : 0;
+#pragma unroll
+		for (int k = 0; k < 8; k++) v[k] <<= sh;
 	} else if (SRC == SRC_S16) {
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
