@@ -469,6 +469,7 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 		fwd_fn fn = pick_fwd(sh, g.trans, src);
 		if (!fn) return set_err(RIC_E_UNSUPPORTED, "forward: unsupported level type combination");
 		const long long njobs = (long long)P.nstrips * P.nsegs * nplanes * n;
+		if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "forward: batch too large for one launch");
 		const int wpb = fwd_warps(sh);
 		P.counter = ctr + lv;
 		const unsigned grid = (unsigned)std::min<long long>((njobs + wpb - 1) / wpb, (long long)c->sm_count * 4);
@@ -536,6 +537,7 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		inv_fn fn = pick_inv(sh, g.trans, dst);
 		if (!fn) return set_err(RIC_E_UNSUPPORTED, "inverse: unsupported level type combination");
 		const long long njobs = (long long)P.nstrips * P.nsegs * jplanes * n;
+		if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "inverse: batch too large for one launch");
 		P.counter = ctr + lv;
 		if (dst == DST_U8_RGB) {
 			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * 3);

@@ -329,12 +329,16 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<tru
 								m = pass ? i + 1 : m;
 							}
 						} else {
-#pragma unroll
+							// irregular thresholds (Q > 16383: int16 wrap in thr[]): rank every candidate against the
+							// parked keys with the reference's signed compare (:191); rolled, rare, small
+#pragma unroll 1
 							for (int i = 0; i < 16; i++) {
-								if (s[i] != 0) {
-									const int fs = (int)(short)(s[i] >> 4);  // signed C compare, :191
-									if (!(fs < qb->thr[(cnt + i) & 15])) { kstar = s[i]; m = i + 1; }
-								}
+								const int ki = ((const int *)&keys[i >> 2][lane])[i & 3];
+								if (ki == 0) continue;
+								int rank = 0;
+#pragma unroll 1
+								for (int j = 0; j < 16; j++) rank += ((const int *)&keys[j >> 2][lane])[j & 3] > ki;
+								if (!((int)(short)(ki >> 4) < qb->thr[(cnt + rank) & 15]) && rank + 1 > m) { m = rank + 1; kstar = ki; }
 							}
 						}
 					}
@@ -385,14 +389,14 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<tru
 
 // One job = one (image, plane, row segment, strip); see the header comment.
 template <bool SH, int TRANS, int SRC>
-__device__ __forceinline__ void fwd_job(const FwdParams &P, long long job, Ring<SH> &rg, KeyRows &keys,
+__device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<SH> &rg, KeyRows &keys,
                                         const QuantBand (&s_qb)[2][3], int lane)
 {
 	// plane fastest: the planes of one RGB strip share their u8 loads through L1
-	const int plane = (int)(job % P.nplanes); job /= P.nplanes;
-	const int sx = (int)(job % P.nstrips); job /= P.nstrips;
-	const int sy = (int)(job % P.nsegs);
-	const int img = (int)(job / P.nsegs);
+	const int plane = (int)(job % (unsigned)P.nplanes); job /= (unsigned)P.nplanes;  // (job ids fit 32 bits: host checks)
+	const int sx = (int)(job % (unsigned)P.nstrips); job /= (unsigned)P.nstrips;
+	const int sy = (int)(job % (unsigned)P.nsegs);
+	const int img = (int)(job / (unsigned)P.nsegs);
 
 	const int w = P.w, h = P.h;
 	const int x0 = sx * STRIP_W;
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 		if (lane == 0) job = atomicAdd(P.counter, 1ull);
 		job = __shfl_sync(FULL, job, 0);
 		if ((long long)job >= njobs) break;
-		fwd_job<SH, TRANS, SRC>(P, (long long)job, s_ring[wib], s_keys[SH ? wib : 0], s_qb, lane);
+		fwd_job<SH, TRANS, SRC>(P, (unsigned)job, s_ring[wib], s_keys[SH ? wib : 0], s_qb, lane);
 	}
 }
 
