@@ -392,3 +392,25 @@ def test_decode_stage_full_range_arenas(ch, q, trans):
     with capi.Context(w, h, ch, 5, trans=trans) as c:
         got = c.decode_u8(arenas, 1, q)[0]
     assert np.array_equal(got, o.decode_image(arenas, ch, q))
+
+
+def test_bench_decode_input_preparation_matches_oracle_unfold():
+    """bench.py prepares its decode input with torch ops (it may not call the oracle): check that
+    helper against rico_unfold, i.e. against what the reference's DecodeBand leaves in the bands."""
+    import importlib.util
+    import os
+    import torch
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w, h, ch, q = 320, 200, 3, 9
+    img = synth_image(0, w, h, ch)
+    o = oraclebind.Oracle(w, h, 5)
+    with capi.Context(w, h, ch, 5) as c:
+        arenas = c.encode_u8(img[None], q)
+        t = torch.from_numpy(arenas.copy()).cuda()
+        bench.unfold_arenas_(c, t, 1)
+        got = t.cpu().numpy()
+    for p in range(ch):
+        o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+    assert np.array_equal(got, arenas)
