@@ -3,18 +3,19 @@
 //
 // Replaces, for one level of every plane of a batch of images:
 //   RGBtoYCoCg / gray shift        src/ric/ric.cpp:76-91,143-148      (SRC_U8_*)
-//   CWavelet2D::Transform97/53     src/lib/wavelet2d.cpp:407-492,636-692 (+TransLine :320-359,:593-611)
+//   CWavelet2D::Transform97/53/Haar src/lib/wavelet2d.cpp:407-492,636-692,788-819 (+TransLine :320-359,:593-611,:766-775)
 //   short->int widening            src/lib/wavelet2d.cpp:938-950
 //   CBandCodec::buildTree          src/lib/bandcodec.cpp:239-322 (this level's D/H/V bands)
 //   CBand::TSUQ (LL, last level)   src/lib/band.h:65-92
 //
-// Work decomposition: one WARP per (image, plane, row segment, 240-column strip).  A lane holds 8
-// consecutive columns; the horizontal lifting takes its neighbours from warp shuffles, the
-// vertical lifting is a streaming filter whose 4-row state lives in registers while the warp
-// walks down its segment two rows at a time.  Finished coefficients are collected per lane into
-// 4x4 blocks (exactly the reference's block grid: strip and segment origins are multiples of 8
-// level samples), quantised in registers and written once, in the band layout the entropy coder
-// reads.  No shared-memory staging of samples, no block-level synchronisation in the main loop.
+// Work decomposition: one warp JOB per (image, plane, row segment, 240-column strip); persistent
+// warps claim jobs from a global counter.  A lane holds 8 consecutive columns; the horizontal
+// lifting takes its neighbours from warp shuffles, the vertical lifting is a streaming filter whose
+// 4-row state lives in registers while the warp walks down its segment two rows at a time.
+// Finished band rows go to a lane-private shared-memory ring; every fourth iteration each lane owns
+// complete 4x4 blocks (exactly the reference's block grid: strip and segment origins are multiples
+// of 8 level samples), quantises them and writes them once, in the band layout the entropy coder
+// reads.  No block-level synchronisation in the main loop.
 #pragma once
 #include <type_traits>
 
