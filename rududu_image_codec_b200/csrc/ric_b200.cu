@@ -205,11 +205,11 @@ static int choose_seg_rows(const ric_ctx *c, int w, int h, long long planes_imag
 {
 	const long long nstrips = (w + STRIP_W - 1) / STRIP_W;
 	const long long slots = c->target_warps > 0 ? c->target_warps : (long long)c->sm_count * jobs_per_sm;
-	static const int cand[] = {256, 192, 160, 128, 112, 96, 80, 64, 56, 48, 40, 32, 24, 16};
-	int best = 16;
+	static const int cand[] = {256, 192, 160, 128, 112, 96, 80, 64, 56, 48, 40, 32, 24, 16, 8};
+	int best = 8;
 	long long best_cost = -1;
 	for (int seg : cand) {
-		if (seg > 16 && seg >= 2 * ((h + 7) & ~7)) continue;  // taller than the level: same as a smaller candidate
+		if (seg > 8 && seg >= 2 * ((h + 7) & ~7)) continue;  // taller than the level: same as a smaller candidate
 		const long long nseg = (h + seg - 1) / seg, rem = h - (nseg - 1) * seg;  // last segment may be short
 		const long long it = (seg < h ? seg : ((h + 7) & ~7)) / 2 + 4, it_last = ((rem + 7) & ~7) / 2 + 4;
 		const long long cols = nstrips * planes_images;          // independent columns of segments
