@@ -542,7 +542,7 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "inverse: batch too large for one launch");
 		P.counter = ctr + lv;
 		if (dst == DST_U8_RGB) {
-			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * 3);
+			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * (6 / INV_RGB_GROUPS));
 			fn<<<grid, INV_RGB_GROUPS * 96, 0, st>>>(P);
 		} else {
 			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_WARPS - 1) / INV_WARPS, (long long)c->sm_count * 4);

@@ -22,7 +22,7 @@ enum { LLSRC_S16 = 0, LLSRC_S32 = 1, LLSRC_BAND = 2 };
 enum { DST_PLANE = 0, DST_U8_GRAY = 1, DST_U8_RGB = 2 };  // DST_PLANE: s16 (short level) / s32 scratch or plane
 
 constexpr int INV_WARPS = 4;       // warps per CTA, independent jobs (DST_PLANE / DST_U8_GRAY)
-constexpr int INV_RGB_GROUPS = 2;  // DST_U8_RGB: groups of 3 warps (Co, Cg, Y of one strip segment) per CTA
+constexpr int INV_RGB_GROUPS = 1;  // DST_U8_RGB: groups of 3 warps (Co, Cg, Y of one strip segment) per CTA; 6 CTAs per SM
 
 struct InvParams {
 	const char *arena;
@@ -293,7 +293,7 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 // Persistent warps with dynamic job fetch (see fwd_level_kernel); for RGB output the three warps of a
 // group claim one job together (broadcast through shared memory under the group's named barrier).
 template <bool SH, int TRANS, int DST>
-__global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_WARPS * 32, DST == DST_U8_RGB ? 3 : 4)
+__global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_WARPS * 32, DST == DST_U8_RGB ? 6 / INV_RGB_GROUPS : 4)
     inv_level_kernel(const __grid_constant__ InvParams P)
 {
 	constexpr bool RGB = DST == DST_U8_RGB;
