@@ -92,6 +92,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
+CPU_SPLIT = {}  # per-stage seconds of the busiest host thread in the last cpu_reference_stage call
+
+
 def cpu_reference_stage(n_images, threads, q):
     """Times the reference's own CPU implementation (oracle/_ref/libric_ref.so) of the stage."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -102,8 +105,13 @@ def cpu_reference_stage(n_images, threads, q):
         return None
     img = np.ascontiguousarray(synth_image(0, W_, H_, CH_))
     L = refbind.lib()
+    split = (ctypes.c_double * 3)()
     t_enc = L.ref_bench_stage(img.ctypes.data, W_, H_, CH_, q, 0, LEVELS_, LEVELS_ - 4, n_images, threads, 0)
+    L.ref_bench_stage_split(split)
+    CPU_SPLIT["encode_s"] = {"colour": split[0], "Transform": split[1], "buildTree+TSUQ": split[2]}
     t_dec = L.ref_bench_stage(img.ctypes.data, W_, H_, CH_, q, 0, LEVELS_, LEVELS_ - 4, n_images, threads, 1)
+    L.ref_bench_stage_split(split)
+    CPU_SPLIT["decode_s"] = {"TSUQi": split[0], "TransformI": split[1], "colour": split[2]}
     return t_enc, t_dec
 
 
@@ -140,6 +148,7 @@ def run_reference(args):
         "decode_mpix_s": n_images * args.steps * W_ * H_ / td / 1e6,
         "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "stage_split_last_step": dict(CPU_SPLIT),
         "wall_s": wall,
     }
     print(json.dumps(line))
@@ -371,7 +380,8 @@ def run_ours(args):
                     "value": 2.0 * threads * W_ * H_ / (te_ + td_) / 1e6, "unit": "Mpixel/s", "cores": threads,
                     "kind": "reference",
                     "sample": "%d images (one per host thread) of the same %dx%d RGB workload, one pass" % (threads, W_, H_),
-                    "encode_mpix_s": threads * W_ * H_ / te_ / 1e6, "decode_mpix_s": threads * W_ * H_ / td_ / 1e6}
+                    "encode_mpix_s": threads * W_ * H_ / te_ / 1e6, "decode_mpix_s": threads * W_ * H_ / td_ / 1e6,
+                    "stage_split_s": dict(CPU_SPLIT)}
         print(json.dumps(line))
     for p in (p1, p2, p3, p4):
         L.ric_host_free(p)

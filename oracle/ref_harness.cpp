@@ -334,6 +334,10 @@ static void unfold_bands(RefWav &h)
 	}
 }
 
+// per-thread stage seconds: mode 0: [0] colour, [1] Transform, [2] buildTree x3 + LL TSUQ;
+//                           mode 1: [0] TSUQi,  [1] TransformI, [2] inverse colour
+static double g_stage_secs[3];
+
 double ref_bench_stage(const uint8_t *src, int w, int h, int ch, int q, int t, int levels, int level_chg,
                        int n_images, int n_threads, int mode)
 {
@@ -342,12 +346,15 @@ double ref_bench_stage(const uint8_t *src, int w, int h, int ch, int q, int t, i
 	int qc = q ? quants(q + kShift * 5 + kCBoost) : 0, lc = q ? quants(q + kShift * 5 - 7 + kCBoost) : 0;
 	std::vector<std::thread> th;
 	std::vector<double> secs(n_threads, 0.0);
+	std::vector<double> stage(3 * n_threads, 0.0);
+	typedef std::chrono::steady_clock clk;
 	for (int k = 0; k < n_threads; k++) {
 		th.emplace_back([&, k]() {
 			std::vector<short> img(n * ch + 64);
 			std::vector<uint8_t> out(n * ch);
 			std::vector<RefWav> wav(ch);
 			std::vector<std::vector<char>> saved(ch);
+			double *st = &stage[3 * k];
 			for (int c = 0; c < ch; c++) {
 				wav[c].w = new CWavelet2D(w, h, levels, level_chg);
 				wav[c].t = (trans)t;
@@ -355,17 +362,26 @@ double ref_bench_stage(const uint8_t *src, int w, int h, int ch, int q, int t, i
 				for (CWavelet2D *p = wav[c].w; p; p = p->pLow) wav[c].lev.push_back(p);
 				wav[c].nlev = (int)wav[c].lev.size();
 			}
-			auto enc = [&]() {
+			auto enc = [&](double *acc) {
+				auto a = clk::now();
 				forward_colour(src, img.data(), w, h, ch, q);
+				auto b = clk::now();
+				double tt = 0, tq = 0;
 				for (int c = ch - 1; c >= 0; c--) {
+					auto c0 = clk::now();
 					wav[c].w->Transform(img.data() + c * n, w, (trans)t);
+					auto c1 = clk::now();
 					bool luma = (ch == 1) || (c == 2);
 					quant_half(wav[c].w, luma ? ql : qc, luma ? ll : lc);
+					auto c2 = clk::now();
+					tt += std::chrono::duration<double>(c1 - c0).count();
+					tq += std::chrono::duration<double>(c2 - c1).count();
 				}
+				if (acc) { acc[0] += std::chrono::duration<double>(b - a).count(); acc[1] += tt; acc[2] += tq; }
 			};
 			double acc = 0;
 			if (mode == 1) {  // prepare quantised signed bands once and snapshot them
-				enc();
+				enc(nullptr);
 				for (int c = 0; c < ch; c++) {
 					unfold_bands(wav[c]);
 					for (int id = 0; id <= 3 * wav[c].nlev; id++) {
@@ -389,18 +405,27 @@ double ref_bench_stage(const uint8_t *src, int w, int h, int ch, int q, int t, i
 						}
 					}
 				}
-				auto t0 = std::chrono::steady_clock::now();
+				auto t0 = clk::now();
 				if (mode == 0) {
-					enc();
+					enc(st);
 				} else {
+					double td = 0, ti = 0;
 					for (int c = ch - 1; c >= 0; c--) {
 						bool luma = (ch == 1) || (c == 2);
+						auto c0 = clk::now();
 						if (q) wav[c].w->TSUQi(luma ? ql : qc);
+						auto c1 = clk::now();
 						wav[c].w->TransformI(img.data() + (c + 1) * n, w, (trans)t);
+						auto c2 = clk::now();
+						td += std::chrono::duration<double>(c1 - c0).count();
+						ti += std::chrono::duration<double>(c2 - c1).count();
 					}
+					auto c3 = clk::now();
 					inverse_colour(img.data(), out.data(), w, h, ch, q);
+					auto c4 = clk::now();
+					st[0] += td; st[1] += ti; st[2] += std::chrono::duration<double>(c4 - c3).count();
 				}
-				auto t1 = std::chrono::steady_clock::now();
+				auto t1 = clk::now();
 				acc += std::chrono::duration<double>(t1 - t0).count();
 			}
 			secs[k] = acc;
@@ -409,8 +434,13 @@ double ref_bench_stage(const uint8_t *src, int w, int h, int ch, int q, int t, i
 	}
 	for (auto &x : th) x.join();
 	double mx = 0;
-	for (double s : secs) if (s > mx) mx = s;
+	int kmax = 0;
+	for (int k = 0; k < n_threads; k++) if (secs[k] > mx) { mx = secs[k]; kmax = k; }
+	for (int i = 0; i < 3; i++) g_stage_secs[i] = stage[3 * kmax + i];
 	return mx;  // busiest thread's compute time == stage makespan
 }
+
+// stage split of the busiest thread of the last ref_bench_stage call (see g_stage_secs)
+void ref_bench_stage_split(double *out3) { for (int i = 0; i < 3; i++) out3[i] = g_stage_secs[i]; }
 
 }  // extern "C"

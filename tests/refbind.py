@@ -52,6 +52,7 @@ def lib():
         L.ref_decompress.argtypes = [C.c_void_p, C.c_long] + [C.c_int] * 7 + [C.c_void_p]
         L.ref_bench_stage.restype = C.c_double
         L.ref_bench_stage.argtypes = [C.c_void_p] + [C.c_int] * 10
+        L.ref_bench_stage_split.argtypes = [C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
