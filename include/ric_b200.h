@@ -147,6 +147,38 @@ int ric_transform_inv(ric_ctx *ctx, const void *arena, int16_t *plane, int strid
 int ric_header_write(uint8_t *out, int width, int height, int q, int color, int trans);
 int ric_header_parse(const uint8_t *in, int *width, int *height, int *q, int *color, int *trans);
 
+/* ---- host entropy stage of the .ric format ----------------------------------------
+ * The second half of CWavelet2D::CodeBand (src/lib/wavelet2d.cpp:119-159: CBandCodec::pred + tree<encode>
+ * over one shared CMuxCodec, src/lib/muxcodec.cpp) and CWavelet2D::DecodeBand (wavelet2d.cpp:183-221).
+ * HOST code by nature -- one adaptive, serial bit stream per image -- and not a fallback for anything: the
+ * transform/quantiser stage above has no CPU path.  No GPU, no context: the geometry arguments are those of
+ * ric_create, so band offsets equal ric_get_band's.  Re-entrant; run one image per host thread.
+ *
+ * ric_entropy_encode: image_arena = the `channels` plane arenas of ONE image as the encode stage wrote them
+ *   (folded values + markers).  Planes are coded luma first (Y, Cg, Co; ric.cpp:163-168).  The arenas are
+ *   consumed (markers are cleared in place, as the reference does).  out receives the payload exactly as a
+ *   .ric file holds it after the 9-byte header; *size its length.  RIC_E_NOMEM if cap is too small.
+ * ric_entropy_decode: the inverse; image_arena receives signed quantised coefficients (decode-stage input).
+ *   Differs from the reference decoder in one place: a 1-sample edge block of the finest level is read the
+ *   way the encoder wrote it (the reference reader takes one bit too many there). */
+int ric_entropy_encode(int width, int height, int channels, int levels, int level_chg, int align,
+                       void *image_arena, uint8_t *out, size_t cap, size_t *size);
+int ric_entropy_decode(int width, int height, int channels, int levels, int level_chg, int align,
+                       const uint8_t *payload, size_t size, void *image_arena);
+
+/* ---- whole .ric files, batch (CompressImage / DecompressImage without the image-file I/O, ric.cpp:123-251) --
+ * ric_compress_u8: n planar u8 images -> n complete .ric files (header + payload), file i at files + i*stride,
+ *   its length in sizes[i].  The GPU stage runs chunk by chunk on the context's streams while `threads` host
+ *   threads (<= 0: all hardware threads) entropy-code the chunks that have already landed in pinned memory.
+ *   RIC_E_NOMEM if a file would not fit in `stride` bytes (width*height*channels + RIC_HEADER_BYTES always does
+ *   for the reference, which allocates exactly that, ric.cpp:131-132).
+ * ric_decompress_u8: n .ric files of the context's geometry and one common quantiser index -> planar u8.
+ *   RIC_E_ARG if a header disagrees with the context (size, colour, transform) or the q values differ. */
+int ric_compress_u8(ric_ctx *ctx, const uint8_t *src, int n, int q, uint8_t *files, size_t stride, size_t *sizes,
+                    int threads);
+int ric_decompress_u8(ric_ctx *ctx, const uint8_t *files, size_t stride, const size_t *sizes, int n, uint8_t *dst,
+                      int threads);
+
 /* pinned host memory helpers (arenas handed to host entropy threads should be pinned) */
 int ric_host_alloc(void **p, size_t bytes);
 int ric_host_free(void *p);

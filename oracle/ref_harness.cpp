@@ -443,4 +443,33 @@ double ref_bench_stage(const uint8_t *src, int w, int h, int ch, int q, int t, i
 // stage split of the busiest thread of the last ref_bench_stage call (see g_stage_secs)
 void ref_bench_stage_split(double *out3) { for (int i = 0; i < 3; i++) out3[i] = g_stage_secs[i]; }
 
+// CPU baseline of the WHOLE codec (bench.py "codec" figures): the CompressImage / DecompressImage
+// restatements above, one image per thread round-robin.  mode 0: compress n_images copies of src;
+// mode 1: decompress n_images copies of the payload of src.  Returns the busiest thread's seconds.
+double ref_bench_codec(const uint8_t *src, int w, int h, int ch, int q, int t, int levels, int level_chg,
+                       int n_images, int n_threads, int mode)
+{
+	const size_t n = (size_t)w * h * ch;
+	std::vector<uint8_t> payload(n * 2 + 4096);
+	const long psz = ref_compress(src, w, h, ch, q, t, levels, level_chg, payload.data(), (long)payload.size());
+	if (psz < 0) return -1.0;
+	std::vector<std::thread> th;
+	std::vector<double> secs(n_threads, 0.0);
+	typedef std::chrono::steady_clock clk;
+	for (int k = 0; k < n_threads; k++)
+		th.emplace_back([&, k]() {
+			std::vector<uint8_t> out(n * 2 + 4096);
+			auto t0 = clk::now();
+			for (int i = k; i < n_images; i += n_threads) {
+				if (mode == 0) ref_compress(src, w, h, ch, q, t, levels, level_chg, out.data(), (long)out.size());
+				else ref_decompress(payload.data(), psz, w, h, ch, q, t, levels, level_chg, out.data());
+			}
+			secs[k] = std::chrono::duration<double>(clk::now() - t0).count();
+		});
+	for (auto &x : th) x.join();
+	double mx = 0;
+	for (double v : secs) mx = v > mx ? v : mx;
+	return mx;
+}
+
 }  // extern "C"

@@ -23,6 +23,7 @@ EXPORTS = [
     "ric_last_launch_count", "ric_transform", "ric_quant", "ric_tsuq", "ric_tsuqi", "ric_transform_inv",
     "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times",
     "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync", "ric_header_write", "ric_header_parse",
+    "ric_entropy_encode", "ric_entropy_decode", "ric_compress_u8", "ric_decompress_u8",
 ]
 
 
@@ -84,6 +85,10 @@ def lib():
         L.ric_header_write.argtypes = [vp, i, i, i, i, i]
         L.ric_header_parse.argtypes = [vp] + [C.POINTER(i)] * 5
         L.ric_get_level_times.argtypes = [vp, i, C.POINTER(C.c_float), i]
+        L.ric_entropy_encode.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
+        L.ric_entropy_decode.argtypes = [i] * 6 + [vp, sz, vp]
+        L.ric_compress_u8.argtypes = [vp, vp, i, i, vp, sz, vp, i]
+        L.ric_decompress_u8.argtypes = [vp, vp, sz, vp, i, vp, i]
         _lib = L
     return _lib
 
@@ -118,6 +123,30 @@ def header_parse(data):
 
 def _ptr(a):
     return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
+
+
+def entropy_encode(width, height, channels, image_arena, levels=5, level_chg=None, align=32, cap=None):
+    """Host entropy stage: one image's quantised band arenas -> .ric payload (bytes after the header).
+    The arenas are consumed (markers cleared in place).  No GPU involved."""
+    if level_chg is None:
+        level_chg = max(levels - 4, 0)
+    if cap is None:
+        cap = 2 * width * height * channels + 4096
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    _check(lib().ric_entropy_encode(width, height, channels, levels, level_chg, align, _ptr(image_arena),
+                                    _ptr(out), cap, C.byref(n)))
+    return out[:n.value].copy()
+
+
+def entropy_decode(width, height, channels, payload, image_arena, levels=5, level_chg=None, align=32):
+    """Host entropy stage, inverse: .ric payload -> signed quantised band arenas (decode-stage input)."""
+    if level_chg is None:
+        level_chg = max(levels - 4, 0)
+    payload = np.ascontiguousarray(np.frombuffer(bytes(payload), dtype=np.uint8))
+    _check(lib().ric_entropy_decode(width, height, channels, levels, level_chg, align, _ptr(payload),
+                                    payload.size, _ptr(image_arena)))
+    return image_arena
 
 
 class Context:
@@ -197,6 +226,31 @@ class Context:
 
     def sync(self):
         _check(self.L.ric_sync(self.h))
+
+    # ---- whole .ric files -----------------------------------------------------------------------
+    def compress_u8(self, imgs, q, threads=0, stride=None):
+        """imgs: u8 (n, channels, height, width) -> list of n complete .ric files (bytes)."""
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8).reshape(-1, self.channels, self.height, self.width)
+        n = imgs.shape[0]
+        if stride is None:
+            stride = self.width * self.height * self.channels * 2 + 4096
+        files = np.empty((n, stride), dtype=np.uint8)
+        sizes = np.zeros(n, dtype=np.uint64)
+        _check(self.L.ric_compress_u8(self.h, _ptr(imgs), n, q, _ptr(files), stride, _ptr(sizes), threads))
+        return [files[i, :int(sizes[i])].tobytes() for i in range(n)]
+
+    def decompress_u8(self, files, threads=0):
+        """files: list of .ric files (bytes) of this context's geometry -> u8 (n, channels, height, width)."""
+        n = len(files)
+        stride = max(len(f) for f in files)
+        buf = np.zeros((n, stride), dtype=np.uint8)
+        sizes = np.zeros(n, dtype=np.uint64)
+        for i, f in enumerate(files):
+            buf[i, :len(f)] = np.frombuffer(f, dtype=np.uint8)
+            sizes[i] = len(f)
+        out = np.empty((n, self.channels, self.height, self.width), dtype=np.uint8)
+        _check(self.L.ric_decompress_u8(self.h, _ptr(buf), stride, _ptr(sizes), n, _ptr(out), threads))
+        return out
 
     # ---- device-resident variants (pointers are raw device addresses, stream a cudaStream_t) ----
     def encode_u8_device(self, d_src, pitch, n, q, d_arenas, stream=0):

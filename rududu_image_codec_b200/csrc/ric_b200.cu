@@ -5,12 +5,17 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
+#include "ric_entropy.h"
 #include "ric_fwd.cuh"
 #include "ric_host.h"
 #include "ric_inv.cuh"
@@ -45,6 +50,7 @@ struct ric_ctx {
 	size_t src_pitch;
 	char *d_arena;          // [max_batch][channels][arena_bytes]  encode output (padding columns stay zero)
 	char *d_arena_in;       // same size, decode-side input (allocated on first use)
+	char *h_stage;          // pinned [max_batch][channels][arena_bytes]: ric_compress_u8 / ric_decompress_u8 staging
 	unsigned char *d_flags; // [max_batch][channels][flag_bytes]
 	short *d_plane;         // [channels][height][plane_pitch] s16 (plane-level API, slot 0)
 	int plane_pitch;
@@ -245,6 +251,7 @@ int ric_destroy(ric_ctx *c)
 	cudaFree(c->d_src);
 	cudaFree(c->d_arena);
 	cudaFree(c->d_arena_in);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
 	cudaFree(c->d_flags);
 	cudaFree(c->d_plane);
 	cudaFree(c->d_count);
@@ -836,6 +843,145 @@ int ric_transform_inv(ric_ctx *c, const void *arena, int16_t *plane, int stride)
 	                     cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	return RIC_OK;
+}
+
+// ---- host entropy stage (no GPU) ------------------------------------------------------------------
+
+static int entropy_geom(HostGeom &g, int w, int h, int ch, int levels, int level_chg, int align, const char *who)
+{
+	const int rc = geom_init(g, w, h, ch, levels, level_chg, align, RIC_CDF97);  // the transform does not shape the bands
+	return rc ? set_err(rc, "%s: unsupported geometry", who) : RIC_OK;
+}
+
+int ric_entropy_encode(int width, int height, int channels, int levels, int level_chg, int align, void *image_arena,
+                       uint8_t *out, size_t cap, size_t *size)
+{
+	HostGeom g;
+	int rc = entropy_geom(g, width, height, channels, levels, level_chg, align, "ric_entropy_encode");
+	if (rc) return rc;
+	if (!image_arena || !out || !size) return set_err(RIC_E_ARG, "ric_entropy_encode: null");
+	const long n = entropy_encode_image(g, (char *)image_arena, out, cap);
+	if (n < 0) return set_err(RIC_E_NOMEM, "ric_entropy_encode: output buffer too small");
+	*size = (size_t)n;
+	return RIC_OK;
+}
+
+int ric_entropy_decode(int width, int height, int channels, int levels, int level_chg, int align, const uint8_t *payload,
+                       size_t size, void *image_arena)
+{
+	HostGeom g;
+	int rc = entropy_geom(g, width, height, channels, levels, level_chg, align, "ric_entropy_decode");
+	if (rc) return rc;
+	if (!image_arena || !payload) return set_err(RIC_E_ARG, "ric_entropy_decode: null");
+	if (entropy_decode_image(g, payload, size, (char *)image_arena)) return set_err(RIC_E_ARG, "ric_entropy_decode: truncated payload");
+	return RIC_OK;
+}
+
+// ---- whole .ric files: GPU stage + host entropy threads ----------------------------------------------
+
+static int need_stage(ric_ctx *c)
+{
+	if (c->h_stage) return RIC_OK;
+	const size_t bytes = (size_t)c->max_batch * c->g.channels * c->g.arena_bytes;
+	cudaError_t e = cudaHostAlloc((void **)&c->h_stage, bytes, cudaHostAllocDefault);
+	if (e != cudaSuccess) { c->h_stage = nullptr; return set_err(RIC_E_NOMEM, "cudaHostAlloc(staging arenas): %s", cudaGetErrorString(e)); }
+	return RIC_OK;
+}
+
+static int worker_count(int threads, int n)
+{
+	if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+	return std::max(1, std::min(threads, n));
+}
+
+namespace {
+struct LandedQueue {  // images whose arenas have reached pinned memory, in arrival order
+	std::mutex mu;
+	std::condition_variable cv;
+	int ready = 0, next = 0, total = 0;
+	static void landed(void *user, int first, int count)  // CUDA callback thread: no CUDA calls here
+	{
+		LandedQueue *q = (LandedQueue *)user;
+		{ std::lock_guard<std::mutex> l(q->mu); q->ready = std::max(q->ready, first + count); }
+		q->cv.notify_all();
+	}
+	void release_all() { { std::lock_guard<std::mutex> l(mu); ready = total; } cv.notify_all(); }
+	int take()  // next image index, or -1 when all have been handed out
+	{
+		std::unique_lock<std::mutex> l(mu);
+		if (next >= total) return -1;
+		cv.wait(l, [&] { return next < ready; });
+		return next++;
+	}
+};
+}  // namespace
+
+int ric_compress_u8(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *files, size_t stride, size_t *sizes, int threads)
+{
+	int rc = check_batch(c, n, q, "ric_compress_u8");
+	if (rc) return rc;
+	if (!src || !files || !sizes) return set_err(RIC_E_ARG, "ric_compress_u8: null buffer");
+	if (stride < RIC_HEADER_BYTES + 4) return set_err(RIC_E_NOMEM, "ric_compress_u8: stride too small");
+	const HostGeom &g = c->g;
+	CK(cudaSetDevice(c->device));
+	if ((rc = need_stage(c))) return rc;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	LandedQueue queue;
+	queue.total = n;
+	std::atomic<int> failed{0};
+	std::vector<std::thread> pool;
+	const int nw = worker_count(threads, n);
+	for (int t = 0; t < nw; t++)
+		pool.emplace_back([&] {
+			for (int i; (i = queue.take()) >= 0;) {
+				uint8_t *f = files + (size_t)i * stride;
+				ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
+				const long sz = entropy_encode_image(g, c->h_stage + (size_t)i * img_ar, f + RIC_HEADER_BYTES, stride - RIC_HEADER_BYTES);
+				if (sz < 0) { failed = 1; sizes[i] = 0; } else sizes[i] = (size_t)sz + RIC_HEADER_BYTES;
+			}
+		});
+	rc = ric_encode_u8_stream(c, src, n, q, c->h_stage, LandedQueue::landed, &queue);
+	int rc2 = sync_pipe(c);
+	if (rc || rc2) queue.release_all();  // let the workers drain (their output is discarded)
+	for (auto &t : pool) t.join();
+	if (rc) return rc;
+	if (rc2) return rc2;
+	if (failed) return set_err(RIC_E_NOMEM, "ric_compress_u8: a file did not fit in `stride` bytes");
+	return RIC_OK;
+}
+
+int ric_decompress_u8(ric_ctx *c, const uint8_t *files, size_t stride, const size_t *sizes, int n, uint8_t *dst, int threads)
+{
+	int rc = check_batch(c, n, 0, "ric_decompress_u8");
+	if (rc) return rc;
+	if (!files || !sizes || !dst) return set_err(RIC_E_ARG, "ric_decompress_u8: null buffer");
+	const HostGeom &g = c->g;
+	int q = -1;
+	for (int i = 0; i < n; i++) {
+		int w, h, qi, color, trans;
+		if (sizes[i] < RIC_HEADER_BYTES || sizes[i] > stride) return set_err(RIC_E_ARG, "ric_decompress_u8: bad file size");
+		if ((rc = ric_header_parse(files + (size_t)i * stride, &w, &h, &qi, &color, &trans))) return rc;
+		if (w != g.width || h != g.height || color != (g.channels == 3) || trans != g.trans)
+			return set_err(RIC_E_ARG, "ric_decompress_u8: file header does not match the context (size, colour or transform)");
+		if (q >= 0 && qi != q) return set_err(RIC_E_ARG, "ric_decompress_u8: files of one batch must share the quantiser index");
+		q = qi;
+	}
+	CK(cudaSetDevice(c->device));
+	if ((rc = need_stage(c))) return rc;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	std::atomic<int> next{0}, failed{0};
+	std::vector<std::thread> pool;
+	const int nw = worker_count(threads, n);
+	for (int t = 0; t < nw; t++)
+		pool.emplace_back([&] {
+			for (int i; (i = next.fetch_add(1)) < n;) {
+				const uint8_t *f = files + (size_t)i * stride;
+				if (entropy_decode_image(g, f + RIC_HEADER_BYTES, sizes[i] - RIC_HEADER_BYTES, c->h_stage + (size_t)i * img_ar)) failed = 1;
+			}
+		});
+	for (auto &t : pool) t.join();
+	if (failed) return set_err(RIC_E_ARG, "ric_decompress_u8: truncated payload");
+	return ric_decode_u8(c, c->h_stage, n, q, dst);
 }
 
 }  // extern "C"

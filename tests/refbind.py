@@ -53,6 +53,8 @@ def lib():
         L.ref_bench_stage.restype = C.c_double
         L.ref_bench_stage.argtypes = [C.c_void_p] + [C.c_int] * 10
         L.ref_bench_stage_split.argtypes = [C.POINTER(C.c_double)]
+        L.ref_bench_codec.restype = C.c_double
+        L.ref_bench_codec.argtypes = [C.c_void_p] + [C.c_int] * 10
         _lib = L
     return _lib
 

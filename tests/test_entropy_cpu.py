@@ -1,0 +1,116 @@
+"""Host entropy stage of the .ric format against the compiled reference.
+
+No GPU involved on either side: the quantised band arenas come from the reference's transform +
+quantiser, then (a) our ric_entropy_encode must produce the reference's payload byte for byte
+(CompressImage's stream, ric.cpp:123-178) and (b) our ric_entropy_decode must rebuild, from that
+payload, exactly the band contents the reference's DecodeBand leaves (wavelet2d.cpp:183-221)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oraclebind
+import refbind
+import refutil
+from rududu_image_codec_b200 import capi, synth
+
+needs_ref = pytest.mark.skipif(not refbind.available(), reason="compiled reference not built")
+
+
+def _image(w, h, ch, idx=0):
+    return synth.synth_image(idx, w, h, ch)
+
+
+def _ref_decode_arenas(o, payload, ch, trans=0):
+    """DecodeBand for every plane through the reference; returns arenas in the canonical layout."""
+    L = refbind.lib()
+    buf = np.zeros(len(payload) + o.w * o.h * ch * 2 + 4096, dtype=np.uint8)
+    buf[2:2 + len(payload)] = np.frombuffer(payload, dtype=np.uint8)
+    codec = L.ref_codec_new_dec(buf.ctypes.data)
+    out = np.zeros(ch * o.arena_bytes, dtype=np.uint8)
+    for p in ([2, 1, 0] if ch == 3 else [0]):
+        r = refbind.RefWavelet(o.w, o.h, o.g.levels, o.g.level_chg, trans)
+        L.ref_decodeband(r.h, codec)
+        out[p * o.arena_bytes:(p + 1) * o.arena_bytes] = refutil.ref_plane_arena(o, r)
+        r.close()
+    L.ref_codec_free(codec)
+    return out
+
+
+CASES = [
+    # w, h, ch, q, levels, level_chg, trans
+    (512, 512, 1, 9, 5, 1, 0),
+    (256, 192, 3, 9, 5, 1, 0),
+    (246, 131, 3, 5, 5, 1, 0),      # partial blocks right and bottom at several levels
+    (250, 134, 1, 13, 5, 1, 0),
+    (333, 217, 3, 1, 5, 1, 0),
+    (128, 96, 3, 31, 5, 1, 0),      # nearly everything insignificant
+    (200, 120, 1, 0, 5, 1, 1),      # lossless 5/3
+    (200, 120, 3, 0, 5, 1, 1),
+    (320, 240, 1, 9, 6, 2, 0),      # two int levels
+    (320, 240, 1, 9, 3, 0, 0),      # all-short
+    (64, 64, 1, 20, 1, 0, 0),       # a single level: the finest band has no parent
+    (192, 128, 3, 9, 5, 1, 2),      # Haar
+    (1021, 67, 1, 7, 5, 1, 0),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("w,h,ch,q,levels,level_chg,trans", CASES)
+def test_payload_and_decoded_bands_match_reference(w, h, ch, q, levels, level_chg, trans):
+    img = _image(w, h, ch)
+    want = refbind.compress(img, q, trans=trans, levels=levels, level_chg=level_chg)
+    o, arenas = refutil.ref_encode_arenas(img, q, levels=levels, level_chg=level_chg, trans=trans)
+    got = capi.entropy_encode(w, h, ch, arenas.copy(), levels=levels, level_chg=level_chg)
+    assert got.tobytes() == bytes(want)
+    try:
+        ref_dec = _ref_decode_arenas(o, bytes(want), ch, trans)
+    except Exception:
+        pytest.skip("reference decoder failed on its own stream")
+    mine = np.full(ch * o.arena_bytes, 0xA5, dtype=np.uint8)
+    capi.entropy_decode(w, h, ch, bytes(want), mine, levels=levels, level_chg=level_chg)
+    for p in range(ch):
+        for i in range(o.nbands):
+            a = o.band_view(mine[p * o.arena_bytes:(p + 1) * o.arena_bytes], i)
+            b = o.band_view(ref_dec[p * o.arena_bytes:(p + 1) * o.arena_bytes], i)
+            f = o.info(i)
+            assert np.array_equal(a[:, :f["dimx"]], b[:, :f["dimx"]]), (p, i)
+
+
+def test_encoder_reports_small_buffer():
+    img = _image(128, 128, 1)
+    arenas = oraclebind.Oracle(128, 128, 5).encode_image(img, 5)
+    with pytest.raises(capi.RicError) as e:
+        capi.entropy_encode(128, 128, 1, arenas.copy(), cap=64)
+    assert e.value.code == capi.E_NOMEM
+
+
+def test_decoder_rejects_truncated_payload():
+    img = _image(128, 128, 1)
+    o = oraclebind.Oracle(128, 128, 5)
+    want = capi.entropy_encode(128, 128, 1, o.encode_image(img, 5)).tobytes()
+    with pytest.raises(capi.RicError):
+        capi.entropy_decode(128, 128, 1, want[:len(want) // 4], np.zeros(o.arena_bytes, dtype=np.uint8))
+
+
+def test_golden_payloads_from_oracle_arenas(golden):
+    """Known answers of SURVEY Appendix C (payload size + CRC32, signed-arena CRC32; tests/golden/kats.json):
+    band arenas from the oracle's transform+quantiser, payload from the product's entropy stage.  Runs
+    without the compiled reference, so it also pins the entropy stage on the GPU box."""
+    from refutil import crc
+    done = 0
+    for k in golden["kats"]:
+        w, h, ch, q = k["w"], k["h"], k["ch"], k["q"]
+        if w * h * ch > 3840 * 2160 * 3:
+            continue
+        img = synth.synth_image(k["idx"], w, h, ch)
+        o = oraclebind.Oracle(w, h, k["levels"], trans=k["trans"])
+        arenas = o.encode_image(img, q)
+        assert crc(arenas) == k["enc_arena_crc"]
+        payload = capi.entropy_encode(w, h, ch, arenas.copy(), levels=k["levels"])
+        assert (len(payload), crc(payload)) == (k["payload_bytes"], k["payload_crc"]), k
+        back = np.full(arenas.size, 0x3C, dtype=np.uint8)
+        capi.entropy_decode(w, h, ch, payload, back, levels=k["levels"])
+        assert crc(back) == k["dec_arena_crc"], k
+        done += 1
+    assert done >= 5

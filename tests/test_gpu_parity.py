@@ -414,3 +414,67 @@ def test_bench_decode_input_preparation_matches_oracle_unfold():
     for p in range(ch):
         o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
     assert np.array_equal(got, arenas)
+
+
+def test_ric_files_match_golden(golden):
+    """Whole .ric files through ric_compress_u8 (GPU stage + product entropy stage on host threads): header
+    bytes, payload size and CRC32 equal the reference's known answers; ric_decompress_u8
+    of those files gives the reference decoder's pixels."""
+    for k in golden["kats"]:
+        w, h, ch, q = k["w"], k["h"], k["ch"], k["q"]
+        if w * h * ch > 3840 * 2160 * 3 or (w * h * ch > 1 << 22 and q not in (9, 27)):
+            continue
+        img = synth_image(k["idx"], w, h, ch)
+        with capi.Context(w, h, ch, k["levels"], trans=k["trans"]) as c:
+            f = c.compress_u8(img[None], q)[0]
+            assert f[:9] == capi.header_write(w, h, q, int(ch == 3), k["trans"])
+            assert (len(f) - 9, crc(np.frombuffer(f[9:], np.uint8))) == (k["payload_bytes"], k["payload_crc"]), k
+            dec = c.decompress_u8([f])
+            assert crc(dec) == k["dec8_crc"], k
+
+
+@pytest.mark.parametrize("ch,q,threads", [(3, 9, 0), (1, 5, 3), (3, 0, 2)])
+def test_ric_file_batch(ch, q, threads):
+    """A batch of different images: every file equals oracle arenas + entropy stage coded one by one, files come
+    back in order whatever thread finished first, and decompress inverts to the oracle's decoder output."""
+    w, h, n = 400, 300, 13
+    trans = 1 if q == 0 else 0
+    imgs = np.stack([synth_image(20 + i, w, h, ch) for i in range(n)])
+    o = oraclebind.Oracle(w, h, 5, trans=trans)
+    with capi.Context(w, h, ch, 5, trans=trans, max_batch=n) as c:
+        files = c.compress_u8(imgs, q, threads=threads)
+        for i in range(n):
+            arenas = o.encode_image(imgs[i], q)
+            want = capi.entropy_encode(w, h, ch, arenas.copy())
+            assert files[i][:9] == capi.header_write(w, h, q, int(ch == 3), trans)
+            assert files[i][9:] == want.tobytes(), i
+        dec = c.decompress_u8(files, threads=threads)
+        for i in range(n):
+            arenas = o.encode_image(imgs[i], q)
+            for p in range(ch):
+                o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+            assert np.array_equal(dec[i], o.decode_image(arenas, ch, q)), i
+        # a second call on the same context reuses the staging arenas
+        assert c.compress_u8(imgs[:5], q, threads=1) == files[:5]
+
+
+def test_ric_file_errors():
+    w, h = 128, 96
+    img = synth_image(1, w, h, 3)
+    with capi.Context(w, h, 3, 5, max_batch=2) as c:
+        with pytest.raises(capi.RicError) as e:
+            c.compress_u8(img[None], 1, stride=64)
+        assert e.value.code == capi.E_NOMEM
+        f9 = c.compress_u8(img[None], 9)[0]
+        f5 = c.compress_u8(img[None], 5)[0]
+        with pytest.raises(capi.RicError) as e:
+            c.decompress_u8([f9, f5])          # different quantiser index in one batch
+        assert e.value.code == capi.E_ARG
+        with pytest.raises(capi.RicError):
+            c.decompress_u8([b"RUD1" + f9[4:]])  # bad magic
+        with pytest.raises(capi.RicError):
+            c.decompress_u8([f9[:len(f9) // 3]])  # truncated payload
+    with capi.Context(w, h, 1, 5) as c:
+        with pytest.raises(capi.RicError) as e:
+            c.decompress_u8([f9])                # colour file, gray context
+        assert e.value.code == capi.E_ARG
