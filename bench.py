@@ -215,6 +215,42 @@ def single_image_latency(capi, synth_image, dev, w, h, ch, levels, q, iters=10):
             "l2": "flushed before every timed call", "iters": iters}
 
 
+def ric_file_throughput(L, ctx, h_src, h_dst, n, q, with_reference):
+    """Images -> complete .ric files -> images through ric_compress_u8 / ric_decompress_u8: host buffers, GPU
+    stage chunk-pipelined with all host threads running the entropy stage.  The reference's whole
+    CompressImage / DecompressImage (oracle/_ref) is timed beside it, one image per host thread."""
+    import numpy as np
+    threads = os.cpu_count() or 1
+    stride = W_ * H_ * CH_ + 4096
+    files = np.empty(n * stride, dtype=np.uint8)
+    sizes = np.zeros(n, dtype=np.uint64)
+
+    def check(rc):
+        if rc:
+            raise RuntimeError(L.ric_last_error().decode())
+    check(L.ric_compress_u8(ctx.h, h_src.ctypes.data, n, q, files.ctypes.data, stride, sizes.ctypes.data, 0))  # warm-up: pins staging
+    t0 = time.perf_counter()
+    check(L.ric_compress_u8(ctx.h, h_src.ctypes.data, n, q, files.ctypes.data, stride, sizes.ctypes.data, 0))
+    t1 = time.perf_counter()
+    check(L.ric_decompress_u8(ctx.h, files.ctypes.data, stride, sizes.ctypes.data, n, h_dst.ctypes.data, 0))
+    t2 = time.perf_counter()
+    out = {"api": "ric_compress_u8 / ric_decompress_u8 (pageable-free: pinned pixels in, .ric files out and back)",
+           "images": n, "host_threads": threads, "mean_file_bytes": float(sizes.mean()),
+           "compress_mpix_s": n * W_ * H_ / (t1 - t0) / 1e6, "decompress_mpix_s": n * W_ * H_ / (t2 - t1) / 1e6}
+    if with_reference:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import refbind
+        from rududu_image_codec_b200.synth import synth_image
+        if refbind.available():
+            img = np.ascontiguousarray(synth_image(0, W_, H_, CH_))
+            R = refbind.lib()
+            tc = R.ref_bench_codec(img.ctypes.data, W_, H_, CH_, q, 0, LEVELS_, LEVELS_ - 4, threads, threads, 0)
+            td = R.ref_bench_codec(img.ctypes.data, W_, H_, CH_, q, 0, LEVELS_, LEVELS_ - 4, threads, threads, 1)
+            out["reference_cpu"] = {"compress_mpix_s": threads * W_ * H_ / tc / 1e6, "decompress_mpix_s": threads * W_ * H_ / td / 1e6,
+                                    "threads": threads, "sample": "one image per host thread, CompressImage / DecompressImage without file I/O"}
+    return out
+
+
 def pinned_array(ctx_lib, nbytes):
     import numpy as np
     p = ctypes.c_void_p()
@@ -371,6 +407,8 @@ def run_ours(args):
             line["single_image"] = {
                 "3840x2160x3_L5": single_image_latency(capi, synth_image, dev, 3840, 2160, CH_, LEVELS_, q),
                 "8192x8192x1_L6": single_image_latency(capi, synth_image, dev, 8192, 8192, 1, 6, q)}
+        if world == 1:  # whole .ric files: the GPU stage feeding the host entropy stage (SURVEY 8d "separately an e2e number ...")
+            line["ric_files"] = ric_file_throughput(L, ctx, h_src, h_dst, B, q, not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_reference_stage(threads, threads, q)

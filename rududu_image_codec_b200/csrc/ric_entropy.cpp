@@ -107,11 +107,8 @@ struct Tables {
 	}
 };
 
-const Tables &tables()
-{
-	static const Tables t;
-	return t;
-}
+const Tables kTables;  // built when the library is loaded
+inline const Tables &tables() { return kTables; }
 
 // ---------------------------------------------------------------------------------------------
 // Stream multiplexer.  Range-coder bytes and raw bit fields share one byte stream; the range coder's
