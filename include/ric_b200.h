@@ -166,6 +166,22 @@ int ric_entropy_encode(int width, int height, int channels, int levels, int leve
 int ric_entropy_decode(int width, int height, int channels, int levels, int level_chg, int align,
                        const uint8_t *payload, size_t size, void *image_arena);
 
+/* Plane-at-a-time form of the same stage, the granularity of the reference API: ONE coder object shared by
+ * the planes of an image (CMuxCodec, src/lib/muxcodec.h:60-139) and one call per plane (the entropy half of
+ * CodeBand / DecodeBand).  `stream` is laid out like the reference's buffer: bytes 0-1 belong to the coder's
+ * start word (a .ric file drops them, ric.cpp:176,203-205) and the payload starts at stream + 2.
+ *   ric_mux_encoder  = CMuxCodec(pStream, firstWord)        ric_mux_decoder = CMuxCodec(pStream)
+ *   ric_mux_code_plane / ric_mux_decode_plane take ONE plane arena and the plane geometry of ric_create
+ *   ric_mux_finish   = CMuxCodec::endCoding(): *end = offset of the returned pointer from `stream`
+ *   ric_mux_destroy frees either kind. */
+typedef struct ric_mux ric_mux;
+int ric_mux_encoder(ric_mux **mux, uint8_t *stream, size_t cap, unsigned first_word);
+int ric_mux_decoder(ric_mux **mux, const uint8_t *stream, size_t size);
+int ric_mux_code_plane(ric_mux *mux, int width, int height, int levels, int level_chg, int align, void *plane_arena);
+int ric_mux_decode_plane(ric_mux *mux, int width, int height, int levels, int level_chg, int align, void *plane_arena);
+int ric_mux_finish(ric_mux *mux, size_t *end);
+int ric_mux_destroy(ric_mux *mux);
+
 /* ---- whole .ric files, batch (CompressImage / DecompressImage without the image-file I/O, ric.cpp:123-251) --
  * ric_compress_u8: n planar u8 images -> n complete .ric files (header + payload), file i at files + i*stride,
  *   its length in sizes[i].  The GPU stage runs chunk by chunk on the context's streams while `threads` host

@@ -8,11 +8,14 @@
 //   class CBandCodec::buildTree            src/lib/bandcodec.h:42   (here: CWavelet2D::QuantBands)
 //   class CWavelet2D                       src/lib/wavelet2d.h:27-88
 //        CWavelet2D(x, y, level, level_chg, Align), SetWeight, Transform<short>, TransformI<short>,
-//        TSUQ, TSUQi, public DBand/HBand/VBand/LBand, pLow/pHigh chain
+//        CodeBand, DecodeBand, TSUQ, TSUQi, public DBand/HBand/VBand/LBand, pLow/pHigh chain
+//   class CMuxCodec (the constructors and endCoding that ric.cpp uses)   src/lib/muxcodec.h:60-139
 // Differences a maintainer must know (INTEGRATION.md has the full list):
 //   * CodeBand = {quantiser half} + {entropy half}.  The quantiser half (buildTree x3 + LL TSUQ,
 //     wavelet2d.cpp:110-126) is QuantBands(Quant, lambda) here and runs on the GPU; the entropy half
-//     (CBandCodec::pred/tree) stays the reference's host code and reads the same pBand buffers.
+//     (CBandCodec::pred/tree, wavelet2d.cpp:119-159) is this library's host entropy stage
+//     (ric_mux_code_plane) reading the same pBand buffers.  CodeBand() does both, so the call sequence of
+//     CompressImage / DecompressImage (ric.cpp:157-176, 203-225) compiles against these classes as it is.
 //   * Transform() leaves the caller's plane untouched (the reference destroys it).
 //   * Band buffers of all levels live in ONE pinned host arena owned by the top-level object; every
 //     CBand::pBand points into it with the reference's DimXAlign stride and 32-byte alignment.
@@ -47,6 +50,42 @@ public:
 };
 
 typedef CBand CBandCodec;  // the entropy half lives in the reference; the data members are CBand's
+
+// CMuxCodec as ric.cpp uses it: CMuxCodec(pStream, firstWord) to write, CMuxCodec(pStream) to read,
+// endCoding() (muxcodec.cpp:25-64,92-113).  The reference knows no buffer bounds; pass `capacity` when
+// you have it and the writer reports overflow instead of running past the end.
+class CMuxCodec {
+public:
+	CMuxCodec(unsigned char *pStream, unsigned short firstWord, size_t capacity = 0) : base_(pStream), mux_(0)
+	{
+		if (ric_mux_encoder(&mux_, pStream, bound(pStream, capacity), firstWord) < 0) fail();
+	}
+	explicit CMuxCodec(unsigned char *pStream) : base_(pStream), mux_(0)
+	{
+		if (ric_mux_decoder(&mux_, pStream, bound(pStream, 0)) < 0) fail();
+	}
+	~CMuxCodec() { ric_mux_destroy(mux_); }
+	CMuxCodec(const CMuxCodec &) = delete;
+	CMuxCodec &operator=(const CMuxCodec &) = delete;
+
+	unsigned char *endCoding()
+	{
+		size_t end = 0;
+		if (ric_mux_finish(mux_, &end) < 0) fail();
+		return base_ + end;
+	}
+	ric_mux *handle() const { return mux_; }
+
+private:
+	static size_t bound(const unsigned char *p, size_t n)
+	{
+		const size_t room = (size_t)(UINTPTR_MAX - (uintptr_t)p) - 1;
+		return n && n < room ? n : room;
+	}
+	static void fail() { throw std::runtime_error(std::string("rududu_b200: ") + ric_last_error()); }
+	unsigned char *base_;
+	ric_mux *mux_;
+};
 
 class CWavelet2D {
 public:
@@ -114,6 +153,19 @@ public:
 	// TSUQ(Quant, 0.5) on the LL band, on the coefficients the last Transform() left on the GPU.
 	// Afterwards the bands hold exactly what CBandCodec::pred / tree<encode> expect.
 	void QuantBands(int Quant, int lambda) { check(ric_quant(ctx(trans_), Quant, lambda, arena_)); }
+
+	// wavelet2d.cpp:83-159: quantiser half on the GPU, then the entropy half on the host into pCodec's stream.
+	void CodeBand(CMuxCodec *pCodec, int Quant, int lambda)
+	{
+		QuantBands(Quant, lambda);
+		check(ric_mux_code_plane(pCodec->handle(), DimX, DimY, levels_, level_chg_, align_, arena_));
+	}
+
+	// wavelet2d.cpp:183-221: the bands receive signed quantised coefficients, ready for TSUQi + TransformI.
+	void DecodeBand(CMuxCodec *pCodec)
+	{
+		check(ric_mux_decode_plane(pCodec->handle(), DimX, DimY, levels_, level_chg_, align_, arena_));
+	}
 
 	// wavelet2d.cpp:224-246 / :248-268
 	unsigned int TSUQ(int Quant, float Thres)

@@ -241,6 +241,7 @@ unsigned ref_tsuq(void *hv, int Quant, float thres) { return ((RefWav *)hv)->w->
 
 // ---- codec objects -------------------------------------------------------------------
 void *ref_codec_new_enc(unsigned char *buf) { return new CMuxCodec(buf, 0); }
+void *ref_codec_new_enc_word(unsigned char *buf, int first_word) { return new CMuxCodec(buf, (unsigned short)first_word); }
 void *ref_codec_new_dec(unsigned char *buf) { return new CMuxCodec(buf); }
 long ref_codec_end(void *c, unsigned char *buf)
 {

@@ -24,6 +24,8 @@ EXPORTS = [
     "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times",
     "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync", "ric_header_write", "ric_header_parse",
     "ric_entropy_encode", "ric_entropy_decode", "ric_compress_u8", "ric_decompress_u8",
+    "ric_mux_encoder", "ric_mux_decoder", "ric_mux_code_plane", "ric_mux_decode_plane", "ric_mux_finish",
+    "ric_mux_destroy",
 ]
 
 
@@ -88,6 +90,12 @@ def lib():
         L.ric_entropy_encode.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
         L.ric_entropy_decode.argtypes = [i] * 6 + [vp, sz, vp]
         L.ric_compress_u8.argtypes = [vp, vp, i, i, vp, sz, vp, i]
+        L.ric_mux_encoder.argtypes = [C.POINTER(vp), vp, sz, C.c_uint]
+        L.ric_mux_decoder.argtypes = [C.POINTER(vp), vp, sz]
+        L.ric_mux_code_plane.argtypes = [vp] + [i] * 5 + [vp]
+        L.ric_mux_decode_plane.argtypes = [vp] + [i] * 5 + [vp]
+        L.ric_mux_finish.argtypes = [vp, C.POINTER(sz)]
+        L.ric_mux_destroy.argtypes = [vp]
         L.ric_decompress_u8.argtypes = [vp, vp, sz, vp, i, vp, i]
         _lib = L
     return _lib
@@ -147,6 +155,39 @@ def entropy_decode(width, height, channels, payload, image_arena, levels=5, leve
     _check(lib().ric_entropy_decode(width, height, channels, levels, level_chg, align, _ptr(payload),
                                     payload.size, _ptr(image_arena)))
     return image_arena
+
+
+class Mux:
+    """The plane-at-a-time entropy coder object (the reference's CMuxCodec + CodeBand/DecodeBand halves).
+    `stream`: a numpy u8 buffer laid out like the reference's (payload from offset 2)."""
+
+    def __init__(self, stream, encode, first_word=0):
+        self.L, self.h, self.stream = lib(), C.c_void_p(), stream
+        if encode:
+            _check(self.L.ric_mux_encoder(C.byref(self.h), _ptr(stream), stream.size, first_word))
+        else:
+            _check(self.L.ric_mux_decoder(C.byref(self.h), _ptr(stream), stream.size))
+
+    def code_plane(self, width, height, plane_arena, levels=5, level_chg=None, align=32):
+        lc = max(levels - 4, 0) if level_chg is None else level_chg
+        _check(self.L.ric_mux_code_plane(self.h, width, height, levels, lc, align, _ptr(plane_arena)))
+
+    def decode_plane(self, width, height, plane_arena, levels=5, level_chg=None, align=32):
+        lc = max(levels - 4, 0) if level_chg is None else level_chg
+        _check(self.L.ric_mux_decode_plane(self.h, width, height, levels, lc, align, _ptr(plane_arena)))
+
+    def finish(self):
+        n = C.c_size_t()
+        _check(self.L.ric_mux_finish(self.h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self.h:
+            self.L.ric_mux_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class Context:

@@ -877,6 +877,67 @@ int ric_entropy_decode(int width, int height, int channels, int levels, int leve
 	return RIC_OK;
 }
 
+struct ric_mux {
+	MuxEncoder *enc;
+	MuxDecoder *dec;
+};
+
+int ric_mux_encoder(ric_mux **mux, uint8_t *stream, size_t cap, unsigned first_word)
+{
+	if (!mux || !stream || first_word > 0xFFFF) return set_err(RIC_E_ARG, "ric_mux_encoder: bad argument");
+	MuxEncoder *e = mux_encoder_new(stream, cap, first_word);
+	if (!e) return set_err(RIC_E_NOMEM, "ric_mux_encoder: buffer too small");
+	*mux = new ric_mux{e, nullptr};
+	return RIC_OK;
+}
+
+int ric_mux_decoder(ric_mux **mux, const uint8_t *stream, size_t size)
+{
+	if (!mux || !stream) return set_err(RIC_E_ARG, "ric_mux_decoder: null");
+	MuxDecoder *d = mux_decoder_new(stream, size);
+	if (!d) return set_err(RIC_E_ARG, "ric_mux_decoder: stream too short");
+	*mux = new ric_mux{nullptr, d};
+	return RIC_OK;
+}
+
+int ric_mux_code_plane(ric_mux *mux, int width, int height, int levels, int level_chg, int align, void *plane_arena)
+{
+	HostGeom g;
+	if (!mux || !mux->enc || !plane_arena) return set_err(RIC_E_ARG, "ric_mux_code_plane: not an encoder / null arena");
+	int rc = entropy_geom(g, width, height, 1, levels, level_chg, align, "ric_mux_code_plane");
+	if (rc) return rc;
+	mux_encoder_plane(mux->enc, g, (char *)plane_arena);
+	return RIC_OK;
+}
+
+int ric_mux_decode_plane(ric_mux *mux, int width, int height, int levels, int level_chg, int align, void *plane_arena)
+{
+	HostGeom g;
+	if (!mux || !mux->dec || !plane_arena) return set_err(RIC_E_ARG, "ric_mux_decode_plane: not a decoder / null arena");
+	int rc = entropy_geom(g, width, height, 1, levels, level_chg, align, "ric_mux_decode_plane");
+	if (rc) return rc;
+	if (mux_decoder_plane(mux->dec, g, (char *)plane_arena)) return set_err(RIC_E_ARG, "ric_mux_decode_plane: truncated stream");
+	return RIC_OK;
+}
+
+int ric_mux_finish(ric_mux *mux, size_t *end)
+{
+	if (!mux || !mux->enc || !end) return set_err(RIC_E_ARG, "ric_mux_finish: not an encoder / null");
+	const long n = mux_encoder_finish(mux->enc);
+	if (n < 0) return set_err(RIC_E_NOMEM, "ric_mux_finish: stream buffer too small");
+	*end = (size_t)n;
+	return RIC_OK;
+}
+
+int ric_mux_destroy(ric_mux *mux)
+{
+	if (!mux) return RIC_OK;
+	if (mux->enc) mux_encoder_free(mux->enc);
+	if (mux->dec) mux_decoder_free(mux->dec);
+	delete mux;
+	return RIC_OK;
+}
+
 // ---- whole .ric files: GPU stage + host entropy threads ----------------------------------------------
 
 static int need_stage(ric_ctx *c)

@@ -118,7 +118,7 @@ inline const Tables &tables() { return kTables; }
 // ---------------------------------------------------------------------------------------------
 class MuxWriter {
 public:
-	MuxWriter(uint8_t *out, size_t cap) : wr_(out + 2), lim_(out + cap)
+	MuxWriter(uint8_t *out, size_t cap, unsigned first_word = 0) : wr_(out + 2), lim_(out + cap), low_((uint32_t)first_word << 16)
 	{
 		// The first two range-coder bytes carry the coder's 16-bit start word; a .ric file does not store them.
 		slot_[0] = &lead_[0]; slot_[1] = &lead_[1]; slot_[2] = out; slot_[3] = out + 1;
@@ -151,6 +151,7 @@ public:
 	}
 
 	bool overflow() const { return overflow_; }
+	uint8_t lead(int i) const { return lead_[i]; }
 
 private:
 	inline uint8_t *claim()
@@ -197,7 +198,7 @@ private:
 	uint8_t *wr_, *lim_;
 	uint8_t *slot_[4];
 	unsigned head_ = 0;
-	uint32_t low_ = 0, range_ = kMinRange << 4;
+	uint32_t low_, range_ = kMinRange << 4;
 	uint32_t acc_ = 0;
 	unsigned nacc_ = 0;
 	uint8_t *parked_ = 0;
@@ -704,6 +705,44 @@ long entropy_encode_image(const HostGeom &g, char *image_arena, uint8_t *out, si
 	uint8_t *end = w.finish();
 	return w.overflow() ? -1 : (long)(end - out);
 }
+
+// ---- plane-at-a-time objects (the reference's CMuxCodec + CodeBand / DecodeBand granularity) ----
+struct MuxEncoder {
+	uint8_t *stream;
+	MuxWriter w;
+	MuxEncoder(uint8_t *s, size_t cap, unsigned first_word) : stream(s), w(s + 2, cap - 2, first_word) {}
+};
+struct MuxDecoder {
+	MuxReader r;
+	MuxDecoder(const uint8_t *s, size_t size) : r(s + 2, size - 2) {}
+};
+
+MuxEncoder *mux_encoder_new(uint8_t *stream, size_t cap, unsigned first_word)
+{
+	return cap < 8 ? nullptr : new MuxEncoder(stream, cap, first_word);
+}
+void mux_encoder_plane(MuxEncoder *m, const HostGeom &g, char *plane_arena)
+{
+	WPort io(m->w);
+	walk_plane(io, g, plane_arena);
+}
+long mux_encoder_finish(MuxEncoder *m)
+{
+	uint8_t *end = m->w.finish();
+	m->stream[0] = m->w.lead(0);
+	m->stream[1] = m->w.lead(1);
+	return m->w.overflow() ? -1 : (long)(end - m->stream);
+}
+void mux_encoder_free(MuxEncoder *m) { delete m; }
+
+MuxDecoder *mux_decoder_new(const uint8_t *stream, size_t size) { return size < 4 ? nullptr : new MuxDecoder(stream, size); }
+int mux_decoder_plane(MuxDecoder *m, const HostGeom &g, char *plane_arena)
+{
+	RPort io(m->r);
+	walk_plane(io, g, plane_arena);
+	return m->r.overrun() ? -1 : 0;
+}
+void mux_decoder_free(MuxDecoder *m) { delete m; }
 
 int entropy_decode_image(const HostGeom &g, const uint8_t *payload, size_t size, char *image_arena)
 {

@@ -29,4 +29,18 @@ long entropy_encode_image(const HostGeom &g, char *image_arena, uint8_t *out, si
 // `payload` need not be padded.  Returns 0, or -1 on a truncated / over-long stream.
 int entropy_decode_image(const HostGeom &g, const uint8_t *payload, size_t size, char *image_arena);
 
+// Plane-at-a-time form, the granularity of the reference API: one coder object shared by the planes of an
+// image (CMuxCodec, muxcodec.cpp:25-64), one call per plane (the entropy half of CodeBand / DecodeBand).
+// `stream` is laid out as the reference's buffer: bytes 0-1 carry the coder's start word (a .ric file
+// drops them, ric.cpp:176,203-205), the payload starts at stream + 2.
+struct MuxEncoder;
+struct MuxDecoder;
+MuxEncoder *mux_encoder_new(uint8_t *stream, size_t cap, unsigned first_word);
+void mux_encoder_plane(MuxEncoder *m, const HostGeom &g, char *plane_arena);
+long mux_encoder_finish(MuxEncoder *m);  // offset of the end pointer from `stream` (CMuxCodec::endCoding), -1 on overflow
+void mux_encoder_free(MuxEncoder *m);
+MuxDecoder *mux_decoder_new(const uint8_t *stream, size_t size);
+int mux_decoder_plane(MuxDecoder *m, const HostGeom &g, char *plane_arena);
+void mux_decoder_free(MuxDecoder *m);
+
 }  // namespace ric

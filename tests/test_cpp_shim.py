@@ -12,12 +12,43 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 PKG = os.path.join(ROOT, "rududu_image_codec_b200")
 
 
-def _build(tmp_path):
-    exe = str(tmp_path / "shim_test")
+def _build(tmp_path, name="shim_test"):
+    exe = str(tmp_path / name)
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
-                           os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"), "-L" + PKG, "-lrududu_b200",
+                           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-L" + PKG, "-lrududu_b200",
                            "-Wl,-rpath," + PKG])
     return exe
+
+
+def test_codec_call_sequence_compiles(tmp_path):
+    """ric.cpp's CompressImage / DecompressImage body compiles unchanged against the shim classes."""
+    _build(tmp_path, "codec_test")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,ch,q", [(384, 256, 3, 9), (250, 134, 1, 5)])
+def test_codec_call_sequence_matches_oracle(tmp_path, w, h, ch, q):
+    """CMuxCodec + Transform/CodeBand per plane + endCoding, then DecodeBand/TSUQi/TransformI, through the
+    shim: payload = oracle arenas through the entropy stage, planes = oracle inverse."""
+    from rududu_image_codec_b200 import capi
+    exe = _build(tmp_path, "codec_test")
+    img = synth_image(2, w, h, ch)
+    planes = oraclebind.colour_fwd(img, q)
+    planes.tofile(tmp_path / "planes.s16")
+    r = subprocess.run([exe, str(w), str(h), str(ch), str(q), str(tmp_path / "planes.s16"), str(tmp_path / "payload.bin"),
+                        str(tmp_path / "out.s16")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    o = oraclebind.Oracle(w, h, 5)
+    arenas = o.encode_image(img, q)
+    want = capi.entropy_encode(w, h, ch, arenas.copy())
+    assert np.fromfile(tmp_path / "payload.bin", dtype=np.uint8).tobytes() == want.tobytes()
+    got = np.fromfile(tmp_path / "out.s16", dtype=np.int16).reshape(ch, h, w)
+    for p in range(ch):
+        a = arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes]
+        o.unfold(a)
+        if q:
+            o.tsuqi(a, oraclebind.plane_quant(q, ch, p)[0])
+        assert np.array_equal(got[p], o.inverse(a)), p
 
 
 def test_shim_compiles_and_fails_loudly_without_gpu(tmp_path):

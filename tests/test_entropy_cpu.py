@@ -114,3 +114,56 @@ def test_golden_payloads_from_oracle_arenas(golden):
         assert crc(back) == k["dec_arena_crc"], k
         done += 1
     assert done >= 5
+
+
+@needs_ref
+@pytest.mark.parametrize("ch,first_word", [(3, 0), (1, 0), (1, 0x1234)])
+def test_plane_at_a_time_coder_matches_reference_buffer(ch, first_word):
+    """ric_mux_*: the CMuxCodec-shaped object.  The whole stream buffer -- including bytes 0-1, which carry
+    the coder's start word and never reach a .ric file -- equals the reference's, plane by plane."""
+    w, h, q = 200, 136, 7
+    img = _image(w, h, ch, 4)
+    o, arenas = refutil.ref_encode_arenas(img, q)
+    L = refbind.lib()
+    L.ref_codec_new_enc_word.restype = C.c_void_p
+    L.ref_codec_new_enc_word.argtypes = [C.c_void_p, C.c_int]
+    ref_buf = np.zeros(w * h * ch * 2 + 4096, dtype=np.uint8)
+    codec = L.ref_codec_new_enc_word(ref_buf.ctypes.data, first_word)
+    mine_buf = np.zeros_like(ref_buf)
+    mux = capi.Mux(mine_buf, encode=True, first_word=first_word)
+    for p in ([2, 1, 0] if ch == 3 else [0]):
+        a = arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes]
+        r = refbind.RefWavelet(w, h, 5, 1, 0)
+        for i in range(o.nbands):
+            r.set_band(i, o.band_view(a, i))
+        L.ref_entropy_encode(r.h, codec)
+        r.close()
+        mux.code_plane(w, h, a.copy())
+    n = L.ref_codec_end(codec, ref_buf.ctypes.data)
+    L.ref_codec_free(codec)
+    assert mux.finish() == n
+    mux.close()
+    assert np.array_equal(mine_buf[:n], ref_buf[:n])
+    # and back, plane by plane
+    dec = capi.Mux(mine_buf[:n + 8], encode=False)
+    ref_dec = _ref_decode_arenas(o, bytes(ref_buf[2:n]), ch)
+    for p in ([2, 1, 0] if ch == 3 else [0]):
+        a = np.full(o.arena_bytes, 0x77, dtype=np.uint8)
+        dec.decode_plane(w, h, a)
+        for i in range(o.nbands):
+            f = o.info(i)
+            assert np.array_equal(o.band_view(a, i)[:, :f["dimx"]],
+                                  o.band_view(ref_dec[p * o.arena_bytes:(p + 1) * o.arena_bytes], i)[:, :f["dimx"]])
+    dec.close()
+
+
+def test_mux_argument_checks():
+    buf = np.zeros(64, dtype=np.uint8)
+    enc = capi.Mux(buf, encode=True)
+    with pytest.raises(capi.RicError):
+        enc.decode_plane(64, 64, np.zeros(16, dtype=np.uint8))   # an encoder cannot decode
+    with pytest.raises(capi.RicError):
+        enc.code_plane(8, 8, np.zeros(16, dtype=np.uint8))       # geometry below the codec's minimum
+    enc.close()
+    with pytest.raises(capi.RicError):
+        capi.Mux(np.zeros(4, dtype=np.uint8), encode=True)       # no room for a stream
