@@ -6,8 +6,9 @@
 #include "ric_entropy.h"
 
 #include <string.h>
-
-#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "ric_huff_data.h"
 
@@ -371,8 +372,8 @@ inline uint32_t truncated(Port &io, uint32_t value, uint32_t max)
 	return v;
 }
 
-// Which k of n positions are set, as the index of the combination (muxcodec.cpp:341-401).  `mask` has the
-// first scanned position in bit n-1.
+// Which k of n positions are set, as the index of the combination (muxcodec.cpp:341-401).  Bit i of `mask`
+// is scan position i (row-major); the reference numbers positions from the other end, hence n-1-i.
 template <class Port>
 inline uint32_t combination(Port &io, uint32_t mask, unsigned k, unsigned n)
 {
@@ -384,8 +385,11 @@ inline uint32_t combination(Port &io, uint32_t mask, unsigned k, unsigned n)
 	const uint32_t nshort = T.enum_short[n][k];
 	if (Port::writing) {
 		uint32_t m = flip ? mask ^ all : mask, idx = 0;
-		for (unsigned pos = 0, r = 0; m; pos++, m >>= 1)
-			if (m & 1) idx += T.choose[r++][pos];
+		for (unsigned r = 0; m; r++) {
+			const unsigned i = 31 - (unsigned)__builtin_clz(m);  // last scanned position first
+			idx += T.choose[r][n - 1 - i];
+			m ^= 1u << i;
+		}
 		if (idx < nshort) io.bits(idx, len - 1); else io.bits(idx + nshort, len);
 		return mask;
 	}
@@ -394,7 +398,7 @@ inline uint32_t combination(Port &io, uint32_t mask, unsigned k, unsigned n)
 	uint32_t m = 0;
 	int r = (int)k - 1;
 	for (int pos = (int)n - 1; r >= 0 && pos >= 0; pos--)
-		if (idx >= T.choose[r][pos]) { m |= 1u << pos; idx -= T.choose[r][pos]; r--; }
+		if (idx >= T.choose[r][pos]) { m |= 1u << (n - 1 - pos); idx -= T.choose[r][pos]; r--; }
 	return flip ? m ^ all : m;
 }
 
@@ -524,6 +528,29 @@ void walk_ll(Port &io, BandRef<C> b)
 	}
 }
 
+// Bit i set <=> sample i (row-major) of a full 4x4 block is non-zero.
+inline uint32_t nonzero_mask(const int16_t *blk, int stride)
+{
+#if defined(__SSE2__)
+	const __m128i z = _mm_setzero_si128();
+	const __m128i r01 = _mm_unpacklo_epi64(_mm_loadl_epi64((const __m128i *)blk), _mm_loadl_epi64((const __m128i *)(blk + stride)));
+	const __m128i r23 = _mm_unpacklo_epi64(_mm_loadl_epi64((const __m128i *)(blk + 2 * stride)),
+	                                       _mm_loadl_epi64((const __m128i *)(blk + 3 * stride)));
+	const __m128i zero = _mm_packs_epi16(_mm_cmpeq_epi16(r01, z), _mm_cmpeq_epi16(r23, z));  // 0xFF per zero sample
+	return (uint32_t)~_mm_movemask_epi8(zero) & 0xFFFFu;
+#else
+	uint32_t m = 0;
+	for (int i = 0; i < 16; i++) m |= (uint32_t)(blk[(i >> 2) * stride + (i & 3)] != 0) << i;
+	return m;
+#endif
+}
+inline uint32_t nonzero_mask(const int32_t *blk, int stride)
+{
+	uint32_t m = 0;
+	for (int i = 0; i < 16; i++) m |= (uint32_t)(blk[(i >> 2) * stride + (i & 3)] != 0) << i;
+	return m;
+}
+
 // Coefficients of one block (w x h samples, 16 when full): count k, which positions, then magnitude-1
 // through the geometric model and a raw sign bit each (bandcodec.cpp:347-482).
 template <bool FINE, class Port, class C>
@@ -532,16 +559,16 @@ inline unsigned code_block(Port &io, GeomModel &geo, C *blk, int stride, int w, 
 	const Tables &T = tables();
 	const unsigned n = (unsigned)(w * h);
 	const bool full = n == 16;
-	C val[16];
-	uint32_t mask = 0;
+	uint32_t mask = 0;  // bit i = scan position i
 	unsigned k = 0;
 	if (Port::writing) {
-		const C *r = blk;
-		for (int y = 0; y < h; y++, r += stride)
-			for (int x = 0; x < w; x++) {
-				mask <<= 1;
-				if (r[x] != 0) { val[k++] = r[x]; mask |= 1; }
-			}
+		if (full) mask = nonzero_mask(blk, stride);
+		else {
+			const C *r = blk;
+			for (int y = 0, i = 0; y < h; y++, r += stride)
+				for (int x = 0; x < w; x++, i++) mask |= (uint32_t)(r[x] != 0) << i;
+		}
+		k = (unsigned)__builtin_popcount(mask);
 	}
 	if (full) {
 		if constexpr (Port::writing) {
@@ -556,21 +583,17 @@ inline unsigned code_block(Port &io, GeomModel &geo, C *blk, int stride, int w, 
 		if (k != n) mask = combination(io, mask, k, n);
 		else mask = (1u << n) - 1;
 		const unsigned ctx = full ? k - 1 : T.edge_ctx[n][k - 1];
-		if (Port::writing) {
-			for (unsigned i = 0; i < k; i++) {
-				const uint32_t u = sizeof(C) == 2 ? (uint16_t)val[i] : (uint32_t)val[i];
+		for (uint32_t m = mask; m; m &= m - 1) {  // set positions in scan order
+			const unsigned i = (unsigned)__builtin_ctz(m);
+			C *p = full ? blk + (i >> 2) * stride + (i & 3) : blk + (i / (unsigned)w) * stride + i % (unsigned)w;
+			if (Port::writing) {
+				const uint32_t u = sizeof(C) == 2 ? (uint16_t)*p : (uint32_t)*p;
 				geo.code(io, (u >> 1) - 1, ctx);
 				io.bits(u & 1, 1);
+			} else {
+				const uint32_t mag = geo.code(io, 0, ctx) + 1;
+				*p = (C)unfold_sign_lsb((int)((mag << 1) | io.bits(0, 1)));
 			}
-		} else {
-			C *r = blk;
-			uint32_t probe = 1u << (n - 1);
-			for (int y = 0; y < h; y++, r += stride)
-				for (int x = 0; x < w; x++, probe >>= 1)
-					if (mask & probe) {
-						const uint32_t mag = geo.code(io, 0, ctx) + 1;
-						r[x] = (C)unfold_sign_lsb((int)((mag << 1) | io.bits(0, 1)));
-					}
 		}
 	}
 	return k - (FINE ? 1 : 0);
