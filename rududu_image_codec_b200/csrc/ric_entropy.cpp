@@ -33,6 +33,7 @@ struct CountCode {          // one canonical prefix code over k
 	uint8_t first_rank[17]; // ... rank of the HIGHEST code of that length, and
 	uint8_t count[17];      // ... number of codes of that length
 	uint8_t by_rank[17];
+	uint8_t quick_len[256], quick_sym[256];  // decoder: codes of up to 8 bits, indexed by the next 8 stream bits
 };
 
 struct Tables {
@@ -104,7 +105,11 @@ struct Tables {
 			}
 			c.floor16[L] = (uint16_t)top;
 		}
-		(void)nsym;
+		for (int s = 0; s < nsym; s++) {
+			if (c.len[s] > 8) continue;
+			const unsigned first = (unsigned)c.code[s] << (8 - c.len[s]);
+			for (unsigned i = 0; i < (1u << (8 - c.len[s])); i++) { c.quick_len[first + i] = c.len[s]; c.quick_sym[first + i] = (uint8_t)s; }
+		}
 	}
 };
 
@@ -238,16 +243,21 @@ public:
 	{
 		const uint32_t b0 = rd_ < end_ ? rd_[0] : 0, b1 = rd_ + 1 < end_ ? rd_[1] : 0;
 		const uint32_t win = (((acc_ << 16) | (b0 << 8) | b1) >> nacc_) & 0xFFFF;
-		unsigned L = 1;
-		while (win < c.floor16[L] || !c.count[L]) L++;
-		const int rank = c.first_rank[L] + (int)(((uint32_t)c.floor16[L] + ((uint32_t)c.count[L] << (16 - L)) - 1 - win) >> (16 - L));
+		unsigned L = c.quick_len[win >> 8];
+		int sym;
+		if (L) sym = c.quick_sym[win >> 8];
+		else {
+			L = 9;
+			while (win < c.floor16[L] || !c.count[L]) L++;
+			sym = c.by_rank[c.first_rank[L] + (int)(((uint32_t)c.floor16[L] + ((uint32_t)c.count[L] << (16 - L)) - 1 - win) >> (16 - L))];
+		}
 		if (nacc_ >= L) nacc_ -= L;
 		else {
 			const unsigned need = L - nacc_, nbytes = (need + 7) >> 3;
 			for (unsigned i = 0; i < nbytes; i++) acc_ = next();
 			nacc_ = nbytes * 8 - need;
 		}
-		return c.by_rank[rank];
+		return sym;
 	}
 
 	uint32_t taboo()  // muxcodec.cpp:235-276, taboo length 2
