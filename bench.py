@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--q", type=int, default=Q_)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--files-batch", type=int, default=1024,
+                    help="images in the device-entropy .ric file measurement (1080p RGB; 0 = skip)")
     ap.add_argument("--workload", default="4k", choices=["4k", "1080p"],
                     help="4k: 3840x2160 RGB (BASELINE configs[1] shape, the judged line); 1080p: 1920x1080 RGB (configs[3])")
     args = ap.parse_args()
@@ -251,6 +253,54 @@ def ric_file_throughput(L, ctx, h_src, h_dst, n, q, with_reference):
     return out
 
 
+def ric_file_throughput_device(capi, L, dev_index, n, q):
+    """BASELINE configs[3] shape (1080p RGB, thousands of images; here n of them): images -> .ric files -> images
+    with the entropy stage on the device too (ric_compress_u8_gpu / ric_decompress_u8_gpu).  Pinned host buffers;
+    H2D of the pixels, all kernels, D2H of the finished files (and the reverse) inside the timed region."""
+    import numpy as np
+    from rududu_image_codec_b200.synth import synth_image
+    w, h, ch, distinct = 1920, 1080, 3, 8
+    img_px = w * h * ch
+    stride = img_px // 4 + 4096
+    ctx = capi.Context(w, h, ch, LEVELS_, max_batch=n, device=dev_index)
+    h_src, p1 = pinned_array(L, n * img_px)
+    h_dst, p2 = pinned_array(L, n * img_px)
+    h_files, p3 = pinned_array(L, n * stride)
+    sizes = np.zeros(n, dtype=np.uint64)
+    base = np.stack([synth_image(100 + i, w, h, ch) for i in range(distinct)]).reshape(distinct, -1)
+    v = h_src.reshape(n, img_px)
+    for i in range(n):
+        v[i] = base[i % distinct]
+
+    def check(rc):
+        if rc:
+            raise RuntimeError(L.ric_last_error().decode())
+    out = {"api": "ric_compress_u8_gpu / ric_decompress_u8_gpu (entropy stage on the device, one image per warp)",
+           "workload": "%d images of %dx%d RGB, q=%d (BASELINE configs[3] shape)" % (n, w, h, q), "images": n}
+    try:
+        check(L.ric_compress_u8_gpu(ctx.h, h_src.ctypes.data, n, q, h_files.ctypes.data, stride, sizes.ctypes.data))  # warm-up
+        t0 = time.perf_counter()
+        check(L.ric_compress_u8_gpu(ctx.h, h_src.ctypes.data, n, q, h_files.ctypes.data, stride, sizes.ctypes.data))
+        t1 = time.perf_counter()
+        check(L.ric_decompress_u8_gpu(ctx.h, h_files.ctypes.data, stride, sizes.ctypes.data, n, h_dst.ctypes.data))  # warm-up
+        t2 = time.perf_counter()
+        check(L.ric_decompress_u8_gpu(ctx.h, h_files.ctypes.data, stride, sizes.ctypes.data, n, h_dst.ctypes.data))
+        t3 = time.perf_counter()
+        # one image through the host entropy stage must give the same file (the device runs the same coder source)
+        one = capi.Context(w, h, ch, LEVELS_, device=dev_index)
+        ref_file = one.compress_u8(base[1].reshape(1, ch, h, w), q, threads=1)[0]
+        one.close()
+        got = h_files.reshape(n, stride)[1, :int(sizes[1])].tobytes()
+        out.update({"compress_mpix_s": n * w * h / (t1 - t0) / 1e6, "decompress_mpix_s": n * w * h / (t3 - t2) / 1e6,
+                    "mean_file_bytes": float(sizes.mean()), "h2d_bytes": n * img_px, "d2h_bytes": int(sizes.sum()),
+                    "file_equals_host_entropy_path": got == ref_file})
+    finally:
+        ctx.close()
+        for p in (p1, p2, p3):
+            L.ric_host_free(p)
+    return out
+
+
 def pinned_array(ctx_lib, nbytes):
     import numpy as np
     p = ctypes.c_void_p()
@@ -433,6 +483,8 @@ def run_ours(args):
                 "8192x8192x1_L6": single_image_latency(capi, synth_image, dev, 8192, 8192, 1, 6, q)}
         if world == 1:  # whole .ric files: the GPU stage feeding the host entropy stage (SURVEY 8d "separately an e2e number ...")
             line["ric_files"] = ric_file_throughput(L, ctx, h_src, h_dst, B, q, not args.no_cpu_baseline)
+        if world == 1 and args.files_batch > 0:
+            line["ric_files_device"] = ric_file_throughput_device(capi, L, local, args.files_batch, q)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_reference_stage(threads, threads, q)

@@ -182,6 +182,17 @@ int ric_mux_decode_plane(ric_mux *mux, int width, int height, int levels, int le
 int ric_mux_finish(ric_mux *mux, size_t *end);
 int ric_mux_destroy(ric_mux *mux);
 
+/* The same stage ON THE DEVICE, for large batches: one image per warp, the identical coder source.  The
+ * stream of an image is serial, so this only pays when thousands of images are resident (BASELINE configs[3]);
+ * what it buys is that the band arenas never cross PCIe -- only the finished payloads do.
+ * d_arenas: n image arenas in device memory, as ric_encode_u8_device wrote them (consumed) / as
+ * ric_decode_u8_device reads them (written).  d_out / d_payloads: n slots of `stride` bytes; d_sizes: n
+ * payload lengths (encode writes -1 where `stride` was too small).  Asynchronous on `stream`. */
+int ric_entropy_encode_device(ric_ctx *ctx, void *d_arenas, int n, uint8_t *d_out, size_t stride, long long *d_sizes,
+                              void *stream);
+int ric_entropy_decode_device(ric_ctx *ctx, const uint8_t *d_payloads, size_t stride, const long long *d_sizes, int n,
+                              void *d_arenas, void *stream);
+
 /* ---- whole .ric files, batch (CompressImage / DecompressImage without the image-file I/O, ric.cpp:123-251) --
  * ric_compress_u8: n planar u8 images -> n complete .ric files (header + payload), file i at files + i*stride,
  *   its length in sizes[i].  The GPU stage runs chunk by chunk on the context's streams while `threads` host
@@ -194,6 +205,13 @@ int ric_compress_u8(ric_ctx *ctx, const uint8_t *src, int n, int q, uint8_t *fil
                     int threads);
 int ric_decompress_u8(ric_ctx *ctx, const uint8_t *files, size_t stride, const size_t *sizes, int n, uint8_t *dst,
                       int threads);
+
+/* The same two calls with the entropy stage ON THE DEVICE (ric_entropy_*_device): pixels go up, only finished
+ * files come back (and the reverse), the band arenas stay in HBM.  Meant for batches of hundreds to thousands
+ * of images per call -- the per-image stream is serial, so the device needs many images in flight to beat the
+ * host threads (DESIGN.md section 7 has the measured crossover).  Pinned host buffers recommended. */
+int ric_compress_u8_gpu(ric_ctx *ctx, const uint8_t *src, int n, int q, uint8_t *files, size_t stride, size_t *sizes);
+int ric_decompress_u8_gpu(ric_ctx *ctx, const uint8_t *files, size_t stride, const size_t *sizes, int n, uint8_t *dst);
 
 /* pinned host memory helpers (arenas handed to host entropy threads should be pinned) */
 int ric_host_alloc(void **p, size_t bytes);

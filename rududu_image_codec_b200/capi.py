@@ -25,7 +25,8 @@ EXPORTS = [
     "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync", "ric_header_write", "ric_header_parse",
     "ric_entropy_encode", "ric_entropy_decode", "ric_compress_u8", "ric_decompress_u8",
     "ric_mux_encoder", "ric_mux_decoder", "ric_mux_code_plane", "ric_mux_decode_plane", "ric_mux_finish",
-    "ric_mux_destroy",
+    "ric_mux_destroy", "ric_entropy_encode_device", "ric_entropy_decode_device",
+    "ric_compress_u8_gpu", "ric_decompress_u8_gpu",
 ]
 
 
@@ -90,6 +91,10 @@ def lib():
         L.ric_entropy_encode.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
         L.ric_entropy_decode.argtypes = [i] * 6 + [vp, sz, vp]
         L.ric_compress_u8.argtypes = [vp, vp, i, i, vp, sz, vp, i]
+        L.ric_entropy_encode_device.argtypes = [vp, vp, i, vp, sz, vp, vp]
+        L.ric_entropy_decode_device.argtypes = [vp, vp, sz, vp, i, vp, vp]
+        L.ric_compress_u8_gpu.argtypes = [vp, vp, i, i, vp, sz, vp]
+        L.ric_decompress_u8_gpu.argtypes = [vp, vp, sz, vp, i, vp]
         L.ric_mux_encoder.argtypes = [C.POINTER(vp), vp, sz, C.c_uint]
         L.ric_mux_decoder.argtypes = [C.POINTER(vp), vp, sz]
         L.ric_mux_code_plane.argtypes = [vp] + [i] * 5 + [vp]
@@ -269,7 +274,7 @@ class Context:
         _check(self.L.ric_sync(self.h))
 
     # ---- whole .ric files -----------------------------------------------------------------------
-    def compress_u8(self, imgs, q, threads=0, stride=None):
+    def compress_u8(self, imgs, q, threads=0, stride=None, entropy_on_device=False):
         """imgs: u8 (n, channels, height, width) -> list of n complete .ric files (bytes)."""
         imgs = np.ascontiguousarray(imgs, dtype=np.uint8).reshape(-1, self.channels, self.height, self.width)
         n = imgs.shape[0]
@@ -277,10 +282,13 @@ class Context:
             stride = self.width * self.height * self.channels * 2 + 4096
         files = np.empty((n, stride), dtype=np.uint8)
         sizes = np.zeros(n, dtype=np.uint64)
-        _check(self.L.ric_compress_u8(self.h, _ptr(imgs), n, q, _ptr(files), stride, _ptr(sizes), threads))
+        if entropy_on_device:
+            _check(self.L.ric_compress_u8_gpu(self.h, _ptr(imgs), n, q, _ptr(files), stride, _ptr(sizes)))
+        else:
+            _check(self.L.ric_compress_u8(self.h, _ptr(imgs), n, q, _ptr(files), stride, _ptr(sizes), threads))
         return [files[i, :int(sizes[i])].tobytes() for i in range(n)]
 
-    def decompress_u8(self, files, threads=0):
+    def decompress_u8(self, files, threads=0, entropy_on_device=False):
         """files: list of .ric files (bytes) of this context's geometry -> u8 (n, channels, height, width)."""
         n = len(files)
         stride = max(len(f) for f in files)
@@ -290,7 +298,10 @@ class Context:
             buf[i, :len(f)] = np.frombuffer(f, dtype=np.uint8)
             sizes[i] = len(f)
         out = np.empty((n, self.channels, self.height, self.width), dtype=np.uint8)
-        _check(self.L.ric_decompress_u8(self.h, _ptr(buf), stride, _ptr(sizes), n, _ptr(out), threads))
+        if entropy_on_device:
+            _check(self.L.ric_decompress_u8_gpu(self.h, _ptr(buf), stride, _ptr(sizes), n, _ptr(out)))
+        else:
+            _check(self.L.ric_decompress_u8(self.h, _ptr(buf), stride, _ptr(sizes), n, _ptr(out), threads))
         return out
 
     # ---- device-resident variants (pointers are raw device addresses, stream a cudaStream_t) ----
@@ -299,6 +310,12 @@ class Context:
 
     def decode_u8_device(self, d_arenas, n, q, d_dst, pitch, stream=0):
         _check(self.L.ric_decode_u8_device(self.h, d_arenas, n, q, d_dst, pitch, stream))
+
+    def entropy_encode_device(self, d_arenas, n, d_out, stride, d_sizes, stream=0):
+        _check(self.L.ric_entropy_encode_device(self.h, _ptr(d_arenas), n, _ptr(d_out), stride, _ptr(d_sizes), stream))
+
+    def entropy_decode_device(self, d_payloads, stride, d_sizes, n, d_arenas, stream=0):
+        _check(self.L.ric_entropy_decode_device(self.h, _ptr(d_payloads), stride, _ptr(d_sizes), n, _ptr(d_arenas), stream))
 
     def set_profiling(self, on=True):
         _check(self.L.ric_set_profiling(self.h, int(on)))

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "ric_entropy.h"
+#include "ric_entropy_gpu.cuh"
 #include "ric_fwd.cuh"
 #include "ric_host.h"
 #include "ric_inv.cuh"
@@ -50,6 +51,14 @@ struct ric_ctx {
 	size_t src_pitch;
 	char *d_arena;          // [max_batch][channels][arena_bytes]  encode output (padding columns stay zero)
 	char *d_arena_in;       // same size, decode-side input (allocated on first use)
+	HostGeom *d_geom;       // device copies for the GPU entropy stage (allocated on first use)
+	ent::Tables *d_tables;
+	int *d_bad;
+	uint8_t *d_payload;     // [max_batch][payload_stride] device-side .ric payload slots
+	size_t payload_stride;
+	long long *d_psizes, *h_psizes;  // payload lengths, device and pinned host
+	cudaStream_t ent[8];    // one per chunk: the per-image-serial entropy kernels of different chunks run side by side
+	cudaEvent_t ent_ev[8];
 	char *h_stage;          // pinned [max_batch][channels][arena_bytes]: ric_compress_u8 / ric_decompress_u8 staging
 	unsigned char *d_flags; // [max_batch][channels][flag_bytes]
 	short *d_plane;         // [channels][height][plane_pitch] s16 (plane-level API, slot 0)
@@ -252,6 +261,16 @@ int ric_destroy(ric_ctx *c)
 	cudaFree(c->d_arena);
 	cudaFree(c->d_arena_in);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
+	cudaFree(c->d_geom);
+	cudaFree(c->d_tables);
+	cudaFree(c->d_bad);
+	cudaFree(c->d_payload);
+	cudaFree(c->d_psizes);
+	if (c->h_psizes) cudaFreeHost(c->h_psizes);
+	for (int i = 0; i < 8; i++) {
+		if (c->ent[i]) cudaStreamDestroy(c->ent[i]);
+		if (c->ent_ev[i]) cudaEventDestroy(c->ent_ev[i]);
+	}
 	cudaFree(c->d_flags);
 	cudaFree(c->d_plane);
 	cudaFree(c->d_count);
@@ -935,6 +954,199 @@ int ric_mux_destroy(ric_mux *mux)
 	if (mux->enc) mux_encoder_free(mux->enc);
 	if (mux->dec) mux_decoder_free(mux->dec);
 	delete mux;
+	return RIC_OK;
+}
+
+// ---- entropy stage on the device (large batches; one image per warp) ---------------------------------
+
+static int need_entropy_tables(ric_ctx *c)
+{
+	if (c->d_tables) return RIC_OK;
+	size_t bytes = 0;
+	const void *host = entropy_tables(&bytes);
+	if (bytes != sizeof(ent::Tables)) return set_err(RIC_E_ARG, "entropy tables: size mismatch");
+	CK(cudaMalloc(&c->d_tables, bytes));
+	CK(cudaMemcpy(c->d_tables, host, bytes, cudaMemcpyHostToDevice));
+	CK(cudaMalloc(&c->d_geom, sizeof(HostGeom)));
+	CK(cudaMemcpy(c->d_geom, &c->g, sizeof(HostGeom), cudaMemcpyHostToDevice));
+	CK(cudaMalloc(&c->d_bad, sizeof(int)));
+	CK(cudaMemset(c->d_bad, 0, sizeof(int)));
+	return RIC_OK;
+}
+
+int ric_entropy_encode_device(ric_ctx *c, void *d_arenas, int n, uint8_t *d_out, size_t stride, long long *d_sizes, void *stream)
+{
+	if (!c || !d_arenas || !d_out || !d_sizes || n < 1 || stride < 8) return set_err(RIC_E_ARG, "ric_entropy_encode_device: bad argument");
+	CK(cudaSetDevice(c->device));
+	int rc = need_entropy_tables(c);
+	if (rc) return rc;
+	entropy_encode_kernel<<<(n + 1) / 2, 64, 0, (cudaStream_t)stream>>>(c->d_geom, c->d_tables, (char *)d_arenas,
+	                                                                     (size_t)c->g.channels * c->g.arena_bytes, d_out, stride, d_sizes, n);
+	CK(cudaGetLastError());
+	return RIC_OK;
+}
+
+int ric_entropy_decode_device(ric_ctx *c, const uint8_t *d_payloads, size_t stride, const long long *d_sizes, int n, void *d_arenas,
+                              void *stream)
+{
+	if (!c || !d_arenas || !d_payloads || !d_sizes || n < 1) return set_err(RIC_E_ARG, "ric_entropy_decode_device: bad argument");
+	CK(cudaSetDevice(c->device));
+	int rc = need_entropy_tables(c);
+	if (rc) return rc;
+	const size_t img_ar = (size_t)c->g.channels * c->g.arena_bytes;
+	CK(cudaMemsetAsync(d_arenas, 0, (size_t)n * img_ar, (cudaStream_t)stream));
+	entropy_decode_kernel<<<(n + 1) / 2, 64, 0, (cudaStream_t)stream>>>(c->d_geom, c->d_tables, d_payloads, stride, d_sizes, (char *)d_arenas,
+	                                                                     img_ar, c->d_bad, n);
+	CK(cudaGetLastError());
+	return RIC_OK;
+}
+
+// ---- whole .ric files with the entropy stage on the device (large batches) -----------------------------
+
+static int need_payload(ric_ctx *c, size_t pstride)
+{
+	int rc = need_entropy_tables(c);
+	if (rc) return rc;
+	if (!c->ent[0])
+		for (int i = 0; i < 8; i++) {
+			CK(cudaStreamCreateWithFlags(&c->ent[i], cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&c->ent_ev[i], cudaEventDisableTiming));
+		}
+	if (!c->d_psizes) {
+		CK(cudaMalloc(&c->d_psizes, sizeof(long long) * c->max_batch));
+		CK(cudaHostAlloc((void **)&c->h_psizes, sizeof(long long) * c->max_batch, cudaHostAllocDefault));
+	}
+	if (pstride > c->payload_stride) {
+		cudaFree(c->d_payload);
+		c->d_payload = nullptr;
+		c->payload_stride = 0;
+		cudaError_t e = cudaMalloc(&c->d_payload, (size_t)c->max_batch * pstride);
+		if (e != cudaSuccess) return set_err(RIC_E_NOMEM, "cudaMalloc(payload slots): %s", cudaGetErrorString(e));
+		c->payload_stride = pstride;
+	}
+	return RIC_OK;
+}
+
+static int sync_ent(ric_ctx *c)
+{
+	for (int i = 0; i < 8; i++) CK(cudaStreamSynchronize(c->ent[i]));
+	return RIC_OK;
+}
+
+int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *files, size_t stride, size_t *sizes)
+{
+	int rc = check_batch(c, n, q, "ric_compress_u8_gpu");
+	if (rc) return rc;
+	if (!src || !files || !sizes) return set_err(RIC_E_ARG, "ric_compress_u8_gpu: null buffer");
+	if (stride < RIC_HEADER_BYTES + 16) return set_err(RIC_E_NOMEM, "ric_compress_u8_gpu: stride too small");
+	const HostGeom &g = c->g;
+	CK(cudaSetDevice(c->device));
+	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	const size_t pstride = std::min(stride - RIC_HEADER_BYTES, (img_px + 15) & ~(size_t)15) & ~(size_t)15;  // the reference's own bound is W*H*C
+	if ((rc = need_payload(c, pstride))) return rc;
+	if ((rc = sync_pipe(c))) return rc;
+	const int step = chunk_images(n);
+	int total = 0, k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		cudaStream_t st = c->pipe[k % 3], es = c->ent[k];
+		CK(copy_pixels(c->d_src + i0 * img_dev, c->src_pitch, src + i0 * img_px, g.width, g.width,
+		               (size_t)m * g.channels * g.height, cudaMemcpyHostToDevice, st));
+		c->img0 = i0;
+		c->cset = k % 3;
+		rc = ric_encode_u8_device(c, c->d_src + i0 * img_dev, c->src_pitch, m, q, c->d_arena + i0 * img_ar, st);
+		c->img0 = 0;
+		c->cset = 3;
+		if (rc) { sync_pipe(c); sync_ent(c); return rc; }
+		total += c->launches + 1;
+		CK(cudaEventRecord(c->ent_ev[k], st));
+		CK(cudaStreamWaitEvent(es, c->ent_ev[k], 0));
+		entropy_encode_kernel<<<(m + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_arena + i0 * img_ar, img_ar,
+		                                                  c->d_payload + (size_t)i0 * c->payload_stride, c->payload_stride, c->d_psizes + i0, m);
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(c->h_psizes + i0, c->d_psizes + i0, sizeof(long long) * m, cudaMemcpyDeviceToHost, es));
+	}
+	c->launches = total;
+	// as each chunk's payload lengths arrive, fetch exactly those bytes (later chunks are still being coded)
+	bool small = false;
+	k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		CK(cudaStreamSynchronize(c->ent[k]));
+		for (int i = i0; i < i0 + m; i++) {
+			uint8_t *f = files + (size_t)i * stride;
+			ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
+			if (c->h_psizes[i] < 0) { small = true; sizes[i] = 0; continue; }
+			sizes[i] = (size_t)c->h_psizes[i] + RIC_HEADER_BYTES;
+			CK(cudaMemcpyAsync(f + RIC_HEADER_BYTES, c->d_payload + (size_t)i * c->payload_stride, (size_t)c->h_psizes[i],
+			                   cudaMemcpyDeviceToHost, c->pipe[k % 3]));
+		}
+	}
+	if ((rc = sync_pipe(c))) return rc;
+	if (small) return set_err(RIC_E_NOMEM, "ric_compress_u8_gpu: a file did not fit in `stride` bytes");
+	return RIC_OK;
+}
+
+int ric_decompress_u8_gpu(ric_ctx *c, const uint8_t *files, size_t stride, const size_t *sizes, int n, uint8_t *dst)
+{
+	int rc = check_batch(c, n, 0, "ric_decompress_u8_gpu");
+	if (rc) return rc;
+	if (!files || !sizes || !dst) return set_err(RIC_E_ARG, "ric_decompress_u8_gpu: null buffer");
+	const HostGeom &g = c->g;
+	int q = -1;
+	size_t longest = 16;
+	for (int i = 0; i < n; i++) {
+		int w, h, qi, color, trans;
+		if (sizes[i] < RIC_HEADER_BYTES || sizes[i] > stride) return set_err(RIC_E_ARG, "ric_decompress_u8_gpu: bad file size");
+		if ((rc = ric_header_parse(files + (size_t)i * stride, &w, &h, &qi, &color, &trans))) return rc;
+		if (w != g.width || h != g.height || color != (g.channels == 3) || trans != g.trans)
+			return set_err(RIC_E_ARG, "ric_decompress_u8_gpu: file header does not match the context (size, colour or transform)");
+		if (q >= 0 && qi != q) return set_err(RIC_E_ARG, "ric_decompress_u8_gpu: files of one batch must share the quantiser index");
+		q = qi;
+		longest = std::max(longest, sizes[i] - RIC_HEADER_BYTES);
+	}
+	CK(cudaSetDevice(c->device));
+	if ((rc = need_payload(c, (longest + 15) & ~(size_t)15))) return rc;
+	if ((rc = need_arena_in(c))) return rc;
+	if ((rc = sync_pipe(c))) return rc;
+	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	CK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->ent[0]));
+	CK(cudaStreamSynchronize(c->ent[0]));
+	const int step = chunk_images(n);
+	int total = 0, k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		cudaStream_t st = c->pipe[k % 3], es = c->ent[k];
+		for (int i = i0; i < i0 + m; i++) {
+			c->h_psizes[i] = (long long)(sizes[i] - RIC_HEADER_BYTES);
+			CK(cudaMemcpyAsync(c->d_payload + (size_t)i * c->payload_stride, files + (size_t)i * stride + RIC_HEADER_BYTES,
+			                   sizes[i] - RIC_HEADER_BYTES, cudaMemcpyHostToDevice, es));
+		}
+		CK(cudaMemcpyAsync(c->d_psizes + i0, c->h_psizes + i0, sizeof(long long) * m, cudaMemcpyHostToDevice, es));
+		CK(cudaMemsetAsync(c->d_arena_in + i0 * img_ar, 0, (size_t)m * img_ar, es));
+		entropy_decode_kernel<<<(m + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_payload + (size_t)i0 * c->payload_stride,
+		                                                  c->payload_stride, c->d_psizes + i0, c->d_arena_in + i0 * img_ar, img_ar, c->d_bad, m);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(c->ent_ev[k], es));
+		CK(cudaStreamWaitEvent(st, c->ent_ev[k], 0));
+		c->img0 = i0;
+		c->cset = k % 3;
+		rc = ric_decode_u8_device(c, c->d_arena_in + i0 * img_ar, m, q, c->d_src + i0 * img_dev, c->src_pitch, st);
+		c->img0 = 0;
+		c->cset = 3;
+		if (rc) { sync_ent(c); sync_pipe(c); return rc; }
+		total += c->launches + 1;
+		CK(copy_pixels(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,
+		               (size_t)m * g.channels * g.height, cudaMemcpyDeviceToHost, st));
+	}
+	c->launches = total;
+	if ((rc = sync_ent(c))) return rc;
+	if ((rc = sync_pipe(c))) return rc;
+	int bad = 0;
+	CK(cudaMemcpy(&bad, c->d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+	if (bad) return set_err(RIC_E_ARG, "ric_decompress_u8_gpu: truncated payload");
 	return RIC_OK;
 }
 

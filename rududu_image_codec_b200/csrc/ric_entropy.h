@@ -43,4 +43,7 @@ MuxDecoder *mux_decoder_new(const uint8_t *stream, size_t size);
 int mux_decoder_plane(MuxDecoder *m, const HostGeom &g, char *plane_arena);
 void mux_decoder_free(MuxDecoder *m);
 
+// The coder's static tables (a POD block) for the device-side copy; used by the GPU entropy stage only.
+const void *entropy_tables(size_t *bytes);
+
 }  // namespace ric

@@ -456,6 +456,9 @@ def test_ric_file_batch(ch, q, threads):
             assert np.array_equal(dec[i], o.decode_image(arenas, ch, q)), i
         # a second call on the same context reuses the staging arenas
         assert c.compress_u8(imgs[:5], q, threads=1) == files[:5]
+        # the same files with the entropy stage on the device, and back
+        assert c.compress_u8(imgs, q, entropy_on_device=True) == files
+        assert np.array_equal(c.decompress_u8(files, entropy_on_device=True), dec)
 
 
 def test_ric_file_errors():
@@ -474,7 +477,58 @@ def test_ric_file_errors():
             c.decompress_u8([b"RUD1" + f9[4:]])  # bad magic
         with pytest.raises(capi.RicError):
             c.decompress_u8([f9[:len(f9) // 3]])  # truncated payload
+        with pytest.raises(capi.RicError) as e:
+            c.compress_u8(img[None], 1, stride=64, entropy_on_device=True)
+        assert e.value.code == capi.E_NOMEM
+        with pytest.raises(capi.RicError):
+            c.decompress_u8([f9[:len(f9) // 3]], entropy_on_device=True)
+        assert np.array_equal(c.decompress_u8([f9], entropy_on_device=True), c.decompress_u8([f9]))
     with capi.Context(w, h, 1, 5) as c:
         with pytest.raises(capi.RicError) as e:
             c.decompress_u8([f9])                # colour file, gray context
         assert e.value.code == capi.E_ARG
+
+
+@pytest.mark.parametrize("ch,q,trans,w,h", [(3, 9, 0, 400, 300), (1, 5, 0, 250, 134), (3, 0, 1, 128, 96)])
+def test_entropy_stage_on_device(ch, q, trans, w, h):
+    """The device entropy stage (one image per warp, same coder source) against the host one: payloads byte
+    for byte from device-resident encode-stage arenas, and back to the signed arenas the decode stage reads."""
+    import torch
+    n = 5
+    imgs = np.stack([synth_image(40 + i, w, h, ch) for i in range(n)])
+    o = oraclebind.Oracle(w, h, 5, trans=trans)
+    stride = w * h * ch * 2 + 4096
+    with capi.Context(w, h, ch, 5, trans=trans, max_batch=n) as c:
+        st = torch.cuda.current_stream().cuda_stream
+        pitch = (w + 7) & ~7
+        src = torch.zeros((n, ch, h, pitch), dtype=torch.uint8, device="cuda")
+        src[..., :w] = torch.from_numpy(imgs).cuda()
+        ar = torch.zeros(n * c.image_arena_bytes, dtype=torch.uint8, device="cuda")
+        c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
+        out = torch.zeros(n * stride, dtype=torch.uint8, device="cuda")
+        sizes = torch.zeros(n, dtype=torch.int64, device="cuda")
+        c.entropy_encode_device(ar.data_ptr(), n, out.data_ptr(), stride, sizes.data_ptr(), st)
+        torch.cuda.synchronize()
+        out_h, sizes_h = out.cpu().numpy().reshape(n, stride), sizes.cpu().numpy()
+        signed = []
+        for i in range(n):
+            arenas = o.encode_image(imgs[i], q)
+            want = capi.entropy_encode(w, h, ch, arenas.copy())
+            assert sizes_h[i] == want.size and out_h[i, :want.size].tobytes() == want.tobytes(), i
+            for p in range(ch):
+                o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
+            signed.append(arenas)
+        back = torch.full((n * c.image_arena_bytes,), 0x5A, dtype=torch.uint8, device="cuda")
+        c.entropy_decode_device(out.data_ptr(), stride, sizes.data_ptr(), n, back.data_ptr(), st)
+        dst = torch.zeros((n, ch, h, pitch), dtype=torch.uint8, device="cuda")
+        c.decode_u8_device(back.data_ptr(), n, q, dst.data_ptr(), pitch, st)
+        torch.cuda.synchronize()
+        assert np.array_equal(back.cpu().numpy(), np.concatenate(signed))
+        for i in range(n):
+            assert np.array_equal(dst[i, :, :, :w].cpu().numpy(), o.decode_image(signed[i], ch, q)), i
+        # too small a slot is reported per image, not written past
+        small = torch.zeros(n * 64, dtype=torch.uint8, device="cuda")
+        c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
+        c.entropy_encode_device(ar.data_ptr(), n, small.data_ptr(), 64, sizes.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert (sizes.cpu().numpy() == -1).all()
