@@ -1182,9 +1182,11 @@ struct LandedQueue {  // images whose arenas have reached pinned memory, in arri
 	int take()  // next image index, or -1 when all have been handed out
 	{
 		std::unique_lock<std::mutex> l(mu);
+		cv.wait(l, [&] { return next < ready || next >= total; });
 		if (next >= total) return -1;
-		cv.wait(l, [&] { return next < ready; });
-		return next++;
+		const int i = next++;
+		if (next >= total) cv.notify_all();  // workers still waiting have nothing left to wait for
+		return i;
 	}
 };
 }  // namespace
