@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -1027,6 +1028,11 @@ static int need_payload(ric_ctx *c, size_t pstride)
 	return RIC_OK;
 }
 
+// Chunks of the device-entropy calls: at most four.  Streams are multiplexed onto a few hardware queues (eight
+// by default, shared with every other stream of the process); with eight entropy streams, stream i+4 was
+// observed to queue behind stream i's 300 ms kernel.
+static int ent_chunk_images(int n) { return n >= 8 ? (n + 3) / 4 : n >= 2 ? (n + 1) / 2 : 1; }
+
 static int sync_ent(ric_ctx *c)
 {
 	for (int i = 0; i < 8; i++) CK(cudaStreamSynchronize(c->ent[i]));
@@ -1046,11 +1052,20 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 	const size_t pstride = std::min(stride - RIC_HEADER_BYTES, (img_px + 15) & ~(size_t)15) & ~(size_t)15;  // the reference's own bound is W*H*C
 	if ((rc = need_payload(c, pstride))) return rc;
 	if ((rc = sync_pipe(c))) return rc;
-	const int step = chunk_images(n);
+	// All the short work first (pixel copies + encode stage, chunk by chunk), the long per-image-serial entropy
+	// kernels after it: streams share a handful of hardware queues, and a copy queued behind a 300 ms kernel of
+	// another stream would wait for it.
+	const int step = ent_chunk_images(n);
 	int total = 0, k = 0;
+	const bool trace = getenv("RIC_TRACE") != nullptr;
+	cudaEvent_t tev[1 + 3 * 8] = {};
+	if (trace) {
+		for (auto &e : tev) CK(cudaEventCreate(&e));
+		CK(cudaEventRecord(tev[0], c->pipe[0]));
+	}
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
-		cudaStream_t st = c->pipe[k % 3], es = c->ent[k];
+		cudaStream_t st = c->pipe[k % 3];
 		CK(copy_pixels(c->d_src + i0 * img_dev, c->src_pitch, src + i0 * img_px, g.width, g.width,
 		               (size_t)m * g.channels * g.height, cudaMemcpyHostToDevice, st));
 		c->img0 = i0;
@@ -1061,19 +1076,34 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 		if (rc) { sync_pipe(c); sync_ent(c); return rc; }
 		total += c->launches + 1;
 		CK(cudaEventRecord(c->ent_ev[k], st));
+		if (trace) CK(cudaEventRecord(tev[1 + 3 * k], st));
+	}
+	k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		cudaStream_t es = c->ent[k];
 		CK(cudaStreamWaitEvent(es, c->ent_ev[k], 0));
+		if (trace) CK(cudaEventRecord(tev[2 + 3 * k], es));
 		entropy_encode_kernel<<<(m + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_arena + i0 * img_ar, img_ar,
 		                                                  c->d_payload + (size_t)i0 * c->payload_stride, c->payload_stride, c->d_psizes + i0, m);
 		CK(cudaGetLastError());
+		if (trace) CK(cudaEventRecord(tev[3 + 3 * k], es));
 		CK(cudaMemcpyAsync(c->h_psizes + i0, c->d_psizes + i0, sizeof(long long) * m, cudaMemcpyDeviceToHost, es));
 	}
 	c->launches = total;
+	const auto t_start = std::chrono::steady_clock::now();
+	auto stamp = [&](const char *what, int idx) {
+		if (trace) fprintf(stderr, "[ric trace] %s %d at %.1f ms\n", what, idx,
+		                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+	};
+	stamp("enqueued", 0);
 	// as each chunk's payload lengths arrive, fetch exactly those bytes (later chunks are still being coded)
 	bool small = false;
 	k = 0;
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
 		CK(cudaStreamSynchronize(c->ent[k]));
+		stamp("chunk coded", k);
 		for (int i = i0; i < i0 + m; i++) {
 			uint8_t *f = files + (size_t)i * stride;
 			ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
@@ -1084,6 +1114,17 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 		}
 	}
 	if ((rc = sync_pipe(c))) return rc;
+	stamp("files fetched", n);
+	if (trace) {
+		for (int j = 0; j < k; j++) {
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * j]);
+			cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * j]);
+			cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * j]);
+			fprintf(stderr, "[ric trace] chunk %d: encode stage done %.1f ms, entropy kernel %.1f .. %.1f ms\n", j, a, b, d);
+		}
+		for (auto &e : tev) cudaEventDestroy(e);
+	}
 	if (small) return set_err(RIC_E_NOMEM, "ric_compress_u8_gpu: a file did not fit in `stride` bytes");
 	return RIC_OK;
 }
@@ -1114,11 +1155,11 @@ int ric_decompress_u8_gpu(ric_ctx *c, const uint8_t *files, size_t stride, const
 	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
 	CK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), c->ent[0]));
 	CK(cudaStreamSynchronize(c->ent[0]));
-	const int step = chunk_images(n);
+	const int step = ent_chunk_images(n);
 	int total = 0, k = 0;
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
-		cudaStream_t st = c->pipe[k % 3], es = c->ent[k];
+		cudaStream_t es = c->ent[k];
 		for (int i = i0; i < i0 + m; i++) {
 			c->h_psizes[i] = (long long)(sizes[i] - RIC_HEADER_BYTES);
 			CK(cudaMemcpyAsync(c->d_payload + (size_t)i * c->payload_stride, files + (size_t)i * stride + RIC_HEADER_BYTES,
@@ -1130,6 +1171,11 @@ int ric_decompress_u8_gpu(ric_ctx *c, const uint8_t *files, size_t stride, const
 		                                                  c->payload_stride, c->d_psizes + i0, c->d_arena_in + i0 * img_ar, img_ar, c->d_bad, m);
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(c->ent_ev[k], es));
+	}
+	k = 0;
+	for (int i0 = 0; i0 < n; i0 += step, k++) {
+		const int m = std::min(step, n - i0);
+		cudaStream_t st = c->pipe[k % 3];
 		CK(cudaStreamWaitEvent(st, c->ent_ev[k], 0));
 		c->img0 = i0;
 		c->cset = k % 3;

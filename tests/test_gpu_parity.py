@@ -532,3 +532,15 @@ def test_entropy_stage_on_device(ch, q, trans, w, h):
         c.entropy_encode_device(ar.data_ptr(), n, small.data_ptr(), 64, sizes.data_ptr(), st)
         torch.cuda.synchronize()
         assert (sizes.cpu().numpy() == -1).all()
+
+
+def test_ric_file_many_workers():
+    """More host workers than images left to hand out, repeatedly: every worker must come home
+    (regression: a worker waiting for an image that another one then took used to wait forever)."""
+    w, h, n = 64, 48, 40
+    imgs = np.stack([synth_image(i, w, h, 1) for i in range(n)])
+    with capi.Context(w, h, 1, 5, max_batch=n) as c:
+        first = c.compress_u8(imgs, 9, threads=16)
+        for _ in range(15):
+            assert c.compress_u8(imgs, 9, threads=16) == first
+        assert np.array_equal(c.decompress_u8(first, threads=16), c.decompress_u8(first, entropy_on_device=True))
