@@ -1052,17 +1052,17 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 	const size_t pstride = std::min(stride - RIC_HEADER_BYTES, (img_px + 15) & ~(size_t)15) & ~(size_t)15;  // the reference's own bound is W*H*C
 	if ((rc = need_payload(c, pstride))) return rc;
 	if ((rc = sync_pipe(c))) return rc;
-	// All the short work first (pixel copies + encode stage, chunk by chunk), the long per-image-serial entropy
-	// kernels after it: streams share a handful of hardware queues, and a copy queued behind a 300 ms kernel of
-	// another stream would wait for it.
-	const int step = ent_chunk_images(n);
+	// Pixel copies + encode stage chunk by chunk on the pipeline streams, then ONE entropy launch over the whole
+	// batch: the stage is latency-bound per image, so it wants every image in flight at once, and entropy kernels
+	// started per chunk were observed to hold back the encode stages of the later chunks (RIC_TRACE timeline).
+	const int step = chunk_images(n);
 	int total = 0, k = 0;
 	const bool trace = getenv("RIC_TRACE") != nullptr;
-	cudaEvent_t tev[1 + 3 * 8] = {};
-	if (trace) {
-		for (auto &e : tev) CK(cudaEventCreate(&e));
-		CK(cudaEventRecord(tev[0], c->pipe[0]));
-	}
+	const auto t_start = std::chrono::steady_clock::now();
+	auto stamp = [&](const char *what, int idx) {
+		if (trace) fprintf(stderr, "[ric trace] %s %d at %.1f ms\n", what, idx,
+		                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+	};
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
 		cudaStream_t st = c->pipe[k % 3];
@@ -1074,57 +1074,34 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 		c->img0 = 0;
 		c->cset = 3;
 		if (rc) { sync_pipe(c); sync_ent(c); return rc; }
-		total += c->launches + 1;
-		CK(cudaEventRecord(c->ent_ev[k], st));
-		if (trace) CK(cudaEventRecord(tev[1 + 3 * k], st));
+		total += c->launches;
 	}
-	k = 0;
-	for (int i0 = 0; i0 < n; i0 += step, k++) {
-		const int m = std::min(step, n - i0);
-		cudaStream_t es = c->ent[k];
-		CK(cudaStreamWaitEvent(es, c->ent_ev[k], 0));
-		if (trace) CK(cudaEventRecord(tev[2 + 3 * k], es));
-		entropy_encode_kernel<<<(m + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_arena + i0 * img_ar, img_ar,
-		                                                  c->d_payload + (size_t)i0 * c->payload_stride, c->payload_stride, c->d_psizes + i0, m);
-		CK(cudaGetLastError());
-		if (trace) CK(cudaEventRecord(tev[3 + 3 * k], es));
-		CK(cudaMemcpyAsync(c->h_psizes + i0, c->d_psizes + i0, sizeof(long long) * m, cudaMemcpyDeviceToHost, es));
+	cudaStream_t es = c->ent[0];
+	for (int i = 0; i < 3; i++) {
+		CK(cudaEventRecord(c->ent_ev[i], c->pipe[i]));
+		CK(cudaStreamWaitEvent(es, c->ent_ev[i], 0));
 	}
-	c->launches = total;
-	const auto t_start = std::chrono::steady_clock::now();
-	auto stamp = [&](const char *what, int idx) {
-		if (trace) fprintf(stderr, "[ric trace] %s %d at %.1f ms\n", what, idx,
-		                   1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
-	};
+	entropy_encode_kernel<<<(n + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_arena, img_ar, c->d_payload, c->payload_stride,
+	                                                  c->d_psizes, n);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(c->h_psizes, c->d_psizes, sizeof(long long) * n, cudaMemcpyDeviceToHost, es));
+	c->launches = total + 1;
 	stamp("enqueued", 0);
-	// as each chunk's payload lengths arrive, fetch exactly those bytes (later chunks are still being coded)
+	if (trace) { sync_pipe(c); stamp("encode stage done", n); }
+	CK(cudaStreamSynchronize(es));
+	stamp("entropy coded", n);
+	// fetch exactly the bytes of every file
 	bool small = false;
-	k = 0;
-	for (int i0 = 0; i0 < n; i0 += step, k++) {
-		const int m = std::min(step, n - i0);
-		CK(cudaStreamSynchronize(c->ent[k]));
-		stamp("chunk coded", k);
-		for (int i = i0; i < i0 + m; i++) {
-			uint8_t *f = files + (size_t)i * stride;
-			ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
-			if (c->h_psizes[i] < 0) { small = true; sizes[i] = 0; continue; }
-			sizes[i] = (size_t)c->h_psizes[i] + RIC_HEADER_BYTES;
-			CK(cudaMemcpyAsync(f + RIC_HEADER_BYTES, c->d_payload + (size_t)i * c->payload_stride, (size_t)c->h_psizes[i],
-			                   cudaMemcpyDeviceToHost, c->pipe[k % 3]));
-		}
+	for (int i = 0; i < n; i++) {
+		uint8_t *f = files + (size_t)i * stride;
+		ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
+		if (c->h_psizes[i] < 0) { small = true; sizes[i] = 0; continue; }
+		sizes[i] = (size_t)c->h_psizes[i] + RIC_HEADER_BYTES;
+		CK(cudaMemcpyAsync(f + RIC_HEADER_BYTES, c->d_payload + (size_t)i * c->payload_stride, (size_t)c->h_psizes[i],
+		                   cudaMemcpyDeviceToHost, c->pipe[i % 3]));
 	}
 	if ((rc = sync_pipe(c))) return rc;
 	stamp("files fetched", n);
-	if (trace) {
-		for (int j = 0; j < k; j++) {
-			float a = 0, b = 0, d = 0;
-			cudaEventElapsedTime(&a, tev[0], tev[1 + 3 * j]);
-			cudaEventElapsedTime(&b, tev[0], tev[2 + 3 * j]);
-			cudaEventElapsedTime(&d, tev[0], tev[3 + 3 * j]);
-			fprintf(stderr, "[ric trace] chunk %d: encode stage done %.1f ms, entropy kernel %.1f .. %.1f ms\n", j, a, b, d);
-		}
-		for (auto &e : tev) cudaEventDestroy(e);
-	}
 	if (small) return set_err(RIC_E_NOMEM, "ric_compress_u8_gpu: a file did not fit in `stride` bytes");
 	return RIC_OK;
 }
