@@ -1226,12 +1226,13 @@ int ric_compress_u8(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *files
 	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
 	LandedQueue queue;
 	queue.total = n;
-	std::atomic<int> failed{0};
+	std::atomic<int> failed{0}, cancelled{0};
 	std::vector<std::thread> pool;
 	const int nw = worker_count(threads, n);
 	for (int t = 0; t < nw; t++)
 		pool.emplace_back([&] {
 			for (int i; (i = queue.take()) >= 0;) {
+				if (cancelled) continue;  // the GPU stage failed: nothing valid to code, just drain the queue
 				uint8_t *f = files + (size_t)i * stride;
 				ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
 				const long sz = entropy_encode_image(g, c->h_stage + (size_t)i * img_ar, f + RIC_HEADER_BYTES, stride - RIC_HEADER_BYTES);
@@ -1240,7 +1241,7 @@ int ric_compress_u8(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *files
 		});
 	rc = ric_encode_u8_stream(c, src, n, q, c->h_stage, LandedQueue::landed, &queue);
 	int rc2 = sync_pipe(c);
-	if (rc || rc2) queue.release_all();  // let the workers drain (their output is discarded)
+	if (rc || rc2) { cancelled = 1; queue.release_all(); }  // let the workers drain
 	for (auto &t : pool) t.join();
 	if (rc) return rc;
 	if (rc2) return rc2;
