@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "ric_entropy.h"
-#include "ric_entropy_gpu.cuh"
+#include "ric_entropy_gpu.h"
 #include "ric_fwd.cuh"
 #include "ric_host.h"
 #include "ric_inv.cuh"
@@ -53,7 +53,7 @@ struct ric_ctx {
 	char *d_arena;          // [max_batch][channels][arena_bytes]  encode output (padding columns stay zero)
 	char *d_arena_in;       // same size, decode-side input (allocated on first use)
 	HostGeom *d_geom;       // device copies for the GPU entropy stage (allocated on first use)
-	ent::Tables *d_tables;
+	void *d_tables;         // ent::Tables, a POD block
 	int *d_bad;
 	uint8_t *d_payload;     // [max_batch][payload_stride] device-side .ric payload slots
 	size_t payload_stride;
@@ -965,7 +965,6 @@ static int need_entropy_tables(ric_ctx *c)
 	if (c->d_tables) return RIC_OK;
 	size_t bytes = 0;
 	const void *host = entropy_tables(&bytes);
-	if (bytes != sizeof(ent::Tables)) return set_err(RIC_E_ARG, "entropy tables: size mismatch");
 	CK(cudaMalloc(&c->d_tables, bytes));
 	CK(cudaMemcpy(c->d_tables, host, bytes, cudaMemcpyHostToDevice));
 	CK(cudaMalloc(&c->d_geom, sizeof(HostGeom)));
@@ -981,9 +980,8 @@ int ric_entropy_encode_device(ric_ctx *c, void *d_arenas, int n, uint8_t *d_out,
 	CK(cudaSetDevice(c->device));
 	int rc = need_entropy_tables(c);
 	if (rc) return rc;
-	entropy_encode_kernel<<<(n + 1) / 2, 64, 0, (cudaStream_t)stream>>>(c->d_geom, c->d_tables, (char *)d_arenas,
-	                                                                     (size_t)c->g.channels * c->g.arena_bytes, d_out, stride, d_sizes, n);
-	CK(cudaGetLastError());
+	CK(launch_entropy_encode(c->d_geom, c->d_tables, (char *)d_arenas, (size_t)c->g.channels * c->g.arena_bytes, d_out, stride, d_sizes, n,
+	                         (cudaStream_t)stream));
 	return RIC_OK;
 }
 
@@ -996,9 +994,8 @@ int ric_entropy_decode_device(ric_ctx *c, const uint8_t *d_payloads, size_t stri
 	if (rc) return rc;
 	const size_t img_ar = (size_t)c->g.channels * c->g.arena_bytes;
 	CK(cudaMemsetAsync(d_arenas, 0, (size_t)n * img_ar, (cudaStream_t)stream));
-	entropy_decode_kernel<<<(n + 1) / 2, 64, 0, (cudaStream_t)stream>>>(c->d_geom, c->d_tables, d_payloads, stride, d_sizes, (char *)d_arenas,
-	                                                                     img_ar, c->d_bad, n);
-	CK(cudaGetLastError());
+	CK(launch_entropy_decode(c->d_geom, c->d_tables, d_payloads, stride, d_sizes, (char *)d_arenas, img_ar, c->d_bad, n,
+	                         (cudaStream_t)stream));
 	return RIC_OK;
 }
 
@@ -1081,9 +1078,7 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 		CK(cudaEventRecord(c->ent_ev[i], c->pipe[i]));
 		CK(cudaStreamWaitEvent(es, c->ent_ev[i], 0));
 	}
-	entropy_encode_kernel<<<(n + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_arena, img_ar, c->d_payload, c->payload_stride,
-	                                                  c->d_psizes, n);
-	CK(cudaGetLastError());
+	CK(launch_entropy_encode(c->d_geom, c->d_tables, c->d_arena, img_ar, c->d_payload, c->payload_stride, c->d_psizes, n, es));
 	CK(cudaMemcpyAsync(c->h_psizes, c->d_psizes, sizeof(long long) * n, cudaMemcpyDeviceToHost, es));
 	c->launches = total + 1;
 	stamp("enqueued", 0);
@@ -1144,9 +1139,8 @@ int ric_decompress_u8_gpu(ric_ctx *c, const uint8_t *files, size_t stride, const
 		}
 		CK(cudaMemcpyAsync(c->d_psizes + i0, c->h_psizes + i0, sizeof(long long) * m, cudaMemcpyHostToDevice, es));
 		CK(cudaMemsetAsync(c->d_arena_in + i0 * img_ar, 0, (size_t)m * img_ar, es));
-		entropy_decode_kernel<<<(m + 1) / 2, 64, 0, es>>>(c->d_geom, c->d_tables, c->d_payload + (size_t)i0 * c->payload_stride,
-		                                                  c->payload_stride, c->d_psizes + i0, c->d_arena_in + i0 * img_ar, img_ar, c->d_bad, m);
-		CK(cudaGetLastError());
+		CK(launch_entropy_decode(c->d_geom, c->d_tables, c->d_payload + (size_t)i0 * c->payload_stride, c->payload_stride, c->d_psizes + i0,
+		                         c->d_arena_in + i0 * img_ar, img_ar, c->d_bad, m, es));
 		CK(cudaEventRecord(c->ent_ev[k], es));
 	}
 	k = 0;

@@ -1,6 +1,6 @@
 // ric_entropy_core.h -- the entropy stage's stream objects, adaptive models and band walkers, written so that
 // the same source compiles for the host (ric_entropy.cpp, one image per thread) and for the device
-// (ric_entropy_gpu.cuh, one image per warp).  See ric_entropy.h for the reference map.
+// (ric_entropy_gpu.cu, one image per warp).  See ric_entropy.h for the reference map.
 //
 // Structure (ours): one MuxWriter / MuxReader per image carries the interleaved range-coder bytes and raw bit
 // fields; small adaptive models (GeomModel, BitModel) are created per band; the band walkers are written once
