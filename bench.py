@@ -482,9 +482,15 @@ def run_ours(args):
                 "3840x2160x3_L5": single_image_latency(capi, synth_image, dev, 3840, 2160, CH_, LEVELS_, q),
                 "8192x8192x1_L6": single_image_latency(capi, synth_image, dev, 8192, 8192, 1, 6, q)}
         if world == 1:  # whole .ric files: the GPU stage feeding the host entropy stage (SURVEY 8d "separately an e2e number ...")
-            line["ric_files"] = ric_file_throughput(L, ctx, h_src, h_dst, B, q, not args.no_cpu_baseline)
+            try:
+                line["ric_files"] = ric_file_throughput(L, ctx, h_src, h_dst, B, q, not args.no_cpu_baseline)
+            except Exception as e:  # secondary figures must not take the headline line down with them
+                line["ric_files"] = {"error": str(e)}
         if world == 1 and args.files_batch > 0:
-            line["ric_files_device"] = ric_file_throughput_device(capi, L, local, args.files_batch, q)
+            try:
+                line["ric_files_device"] = ric_file_throughput_device(capi, L, local, args.files_batch, q)
+            except Exception as e:
+                line["ric_files_device"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_reference_stage(threads, threads, q)
