@@ -475,6 +475,9 @@ def run_ours(args):
                 line["roofline"]["traffic_source"] = "profiles/traffic.json (ncu --set full, scaled per sample to this batch)"
                 if "limiter" in tj:
                     line["roofline"]["limiter"] = tj["limiter"]
+                if "fwd_level0_issue_active_pct" in tj:  # the roof this kernel actually sits under (ncu, same workload)
+                    line["roofline"]["issue_slot_frac"] = tj["fwd_level0_issue_active_pct"] / 100.0
+                    line["roofline"]["alu_pipe_frac"] = tj["fwd_level0_alu_pipe_pct"] / 100.0
             except Exception:
                 pass
         if world == 1:  # the single-image shapes of BASELINE configs[1] and [2] (latency-bound: 5 dependent launches)

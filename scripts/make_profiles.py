@@ -34,6 +34,7 @@ for r in rows[2:]:
     if "fwd_level_kernel<1, 0, 1>" in name:
         out["fwd_level0_bytes_per_launch"] = e["dram_bytes_per_launch"]
         out["fwd_level0_samples_per_launch"] = B * 3840 * 2160 * 3
+        out["fwd_level0_issue_active_pct"], out["fwd_level0_alu_pipe_pct"] = e["issue_active_pct"], e["alu_pipe_pct"]
         out["limiter"] = ("integer issue: ncu ALU pipe %.0f %%, issue slots %.0f %%, DRAM %.0f %% of peak (level-0 forward kernel)"
                           % (e["alu_pipe_pct"], e["issue_active_pct"], e["dram_pct"]))
     if "inv_level_kernel<1, 0, 2>" in name:
