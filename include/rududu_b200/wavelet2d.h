@@ -24,6 +24,9 @@
 // The namespace is rududu_b200 so that the shim can be linked next to the reference library in
 // tests; a drop-in build adds `namespace rududu = rududu_b200;`.
 #pragma once
+#include <stddef.h>
+#include <stdint.h>
+
 #include <stdexcept>
 #include <string>
 
@@ -47,6 +50,40 @@ public:
 	CBand *pParent = 0, *pChild = 0, *pNeighbor[3] = {0, 0, 0};
 	char *pBand = 0;  // points into the owning CWavelet2D's pinned arena
 	band_t type = sshort;
+
+	// Host-side helpers of the reference class (band.h:114-159, band.cpp:162-167): statistics and debugging
+	// aids over the band buffer, not part of the hot path.
+	template <class C>
+	void Mean(float &Mean, float &Var) const
+	{
+		long long sum = 0, sq = 0;
+		const C *p = (const C *)pBand;
+		for (unsigned j = 0; j < DimY; j++, p += DimXAlign)
+			for (unsigned i = 0; i < DimX; i++) { sum += p[i]; sq += (long long)(p[i] * p[i]); }
+		const float n = (float)(DimX * DimY);
+		Mean = (float)sum * Weight / n;
+		Var = (float)(sq - sum * sum) * Weight * Weight / (n * n);
+	}
+	template <class C>
+	void Add(C val)
+	{
+		C *p = (C *)pBand;
+		for (unsigned i = 0; i < BandSize; i++) p[i] = (C)(p[i] + val);
+	}
+	void Clear(bool recurse = false)
+	{
+		const size_t bytes = (size_t)BandSize * (type == sint ? 4 : 2);
+		for (size_t i = 0; i < bytes; i++) pBand[i] = 0;
+		if (recurse && pParent) pParent->Clear(true);
+	}
+	template <class C, class T>
+	void GetBand(T *pOut) const  // samples re-centred on the middle of T's range, rows packed
+	{
+		const C *p = (const C *)pBand;
+		const int mid = 1 << (sizeof(T) * 8 - 1);
+		for (unsigned j = 0; j < DimY; j++, p += DimXAlign, pOut += DimX)
+			for (unsigned i = 0; i < DimX; i++) pOut[i] = (T)(p[i] + mid);
+	}
 };
 
 typedef CBand CBandCodec;  // the entropy half lives in the reference; the data members are CBand's

@@ -64,6 +64,14 @@ int main(int argc, char **argv)
 				Wavelet.TSUQi(ric_quants(Quant + SHIFT * 5 + C_Q_BOOST));
 			}
 			Wavelet.TransformI(out.data() + n, w, Trans);
+			// the reference class's host helpers exist on the shim's bands too
+			std::vector<unsigned char> vis((size_t)Wavelet.HBand.DimX * Wavelet.HBand.DimY);
+			Wavelet.HBand.GetBand<short, unsigned char>(vis.data());
+			float mean, var;
+			Wavelet.HBand.Mean<short>(mean, var);
+			Wavelet.HBand.Add<short>(1);
+			Wavelet.HBand.Clear();
+			if (Wavelet.HBand.pBand[0] != 0) return 3;
 		}
 		f = fopen(argv[7], "wb");
 		fwrite(out.data(), 2, out.size(), f);
