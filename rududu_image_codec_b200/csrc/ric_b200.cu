@@ -706,37 +706,44 @@ int ric_encode_u8(ric_ctx *c, const uint8_t *src, int n, int q, void *arenas)
 	return rc ? rc : sync_pipe(c);
 }
 
+// H2D of the arenas of images [i0, i0+m), decode stage, D2H of their pixels, all on pipeline stream k % 3.
+static int decode_chunk(ric_ctx *c, const void *arenas, int i0, int m, int q, uint8_t *dst, int k)
+{
+	const HostGeom &g = c->g;
+	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
+	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	cudaStream_t st = c->pipe[k % 3];
+	CK(cudaMemcpyAsync(c->d_arena_in + i0 * img_ar, (const char *)arenas + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyHostToDevice, st));
+	c->img0 = i0;
+	c->cset = k % 3;
+	const int rc = ric_decode_u8_device(c, c->d_arena_in + i0 * img_ar, m, q, c->d_src + i0 * img_dev, c->src_pitch, st);
+	c->img0 = 0;
+	c->cset = 3;
+	if (rc) return rc;
+	CK(copy_pixels(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width, (size_t)m * g.channels * g.height,
+	               cudaMemcpyDeviceToHost, st));
+	return RIC_OK;
+}
+
 int ric_decode_u8_stream(ric_ctx *c, const void *arenas, int n, int q, uint8_t *dst, ric_chunk_fn done, void *user)
 {
 	int rc = check_batch(c, n, q, "ric_decode_u8_stream");
 	if (rc) return rc;
 	if (!dst || !arenas) return set_err(RIC_E_ARG, "ric_decode_u8_stream: null buffer");
-	const HostGeom &g = c->g;
 	CK(cudaSetDevice(c->device));
 	if ((rc = need_arena_in(c))) return rc;
 	if ((rc = sync_pipe(c))) return rc;
-	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
-	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
 	const int step = chunk_images(n);
 	c->notes.assign((size_t)(n + step - 1) / step, ric_ctx::ChunkNote{done, user, 0, 0});
 	int total = 0, k = 0;
 	for (int i0 = 0; i0 < n; i0 += step, k++) {
 		const int m = std::min(step, n - i0);
-		cudaStream_t st = c->pipe[k % 3];
-		CK(cudaMemcpyAsync(c->d_arena_in + i0 * img_ar, (const char *)arenas + i0 * img_ar, (size_t)m * img_ar, cudaMemcpyHostToDevice, st));
-		c->img0 = i0;
-		c->cset = k % 3;
-		rc = ric_decode_u8_device(c, c->d_arena_in + i0 * img_ar, m, q, c->d_src + i0 * img_dev, c->src_pitch, st);
-		c->img0 = 0;
-		c->cset = 3;
-		if (rc) { sync_pipe(c); return rc; }
+		if ((rc = decode_chunk(c, arenas, i0, m, q, dst, k))) { sync_pipe(c); return rc; }
 		total += c->launches;
-		CK(copy_pixels(dst + i0 * img_px, g.width, c->d_src + i0 * img_dev, c->src_pitch, g.width,
-		               (size_t)m * g.channels * g.height, cudaMemcpyDeviceToHost, st));
 		if (done) {
 			c->notes[k].first = i0;
 			c->notes[k].count = m;
-			CK(cudaLaunchHostFunc(st, chunk_trampoline, &c->notes[k]));
+			CK(cudaLaunchHostFunc(c->pipe[k % 3], chunk_trampoline, &c->notes[k]));
 		}
 	}
 	c->launches = total;
@@ -1261,7 +1268,16 @@ int ric_decompress_u8(ric_ctx *c, const uint8_t *files, size_t stride, const siz
 	}
 	CK(cudaSetDevice(c->device));
 	if ((rc = need_stage(c))) return rc;
+	if ((rc = need_arena_in(c))) return rc;
+	if ((rc = sync_pipe(c))) return rc;
 	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
+	// Workers take the files in order; as soon as every image of a chunk is decoded the main thread sends that
+	// chunk through the decode stage, while the workers go on with the later chunks.
+	const int step = chunk_images(n), nchunks = (n + step - 1) / step;
+	std::vector<int> left(nchunks);
+	for (int k = 0; k < nchunks; k++) left[k] = std::min(step, n - k * step);
+	std::mutex mu;
+	std::condition_variable cv;
 	std::atomic<int> next{0}, failed{0};
 	std::vector<std::thread> pool;
 	const int nw = worker_count(threads, n);
@@ -1270,11 +1286,24 @@ int ric_decompress_u8(ric_ctx *c, const uint8_t *files, size_t stride, const siz
 			for (int i; (i = next.fetch_add(1)) < n;) {
 				const uint8_t *f = files + (size_t)i * stride;
 				if (entropy_decode_image(g, f + RIC_HEADER_BYTES, sizes[i] - RIC_HEADER_BYTES, c->h_stage + (size_t)i * img_ar)) failed = 1;
+				bool chunk_done;
+				{ std::lock_guard<std::mutex> l(mu); chunk_done = --left[i / step] == 0; }
+				if (chunk_done) cv.notify_all();
 			}
 		});
+	int total = 0;
+	for (int k = 0; k < nchunks && !rc; k++) {
+		{ std::unique_lock<std::mutex> l(mu); cv.wait(l, [&] { return left[k] == 0; }); }
+		if (failed) break;  // a truncated file: its arenas are not worth decoding
+		rc = decode_chunk(c, c->h_stage, k * step, std::min(step, n - k * step), q, dst, k);
+		total += c->launches;
+	}
 	for (auto &t : pool) t.join();
+	const int rc2 = sync_pipe(c);
+	c->launches = total;
+	if (rc) return rc;
 	if (failed) return set_err(RIC_E_ARG, "ric_decompress_u8: truncated payload");
-	return ric_decode_u8(c, c->h_stage, n, q, dst);
+	return rc2;
 }
 
 }  // extern "C"
