@@ -258,6 +258,8 @@ int ric_destroy(ric_ctx *c)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	for (int i = 0; i < 3; i++)
 		if (c->pipe[i]) cudaStreamSynchronize(c->pipe[i]);  // outstanding *_stream chunks and their callbacks
+	for (int i = 0; i < 8; i++)
+		if (c->ent[i]) cudaStreamSynchronize(c->ent[i]);
 	cudaFree(c->d_src);
 	cudaFree(c->d_arena);
 	cudaFree(c->d_arena_in);
