@@ -165,6 +165,13 @@ int ric_entropy_encode(int width, int height, int channels, int levels, int leve
                        void *image_arena, uint8_t *out, size_t cap, size_t *size);
 int ric_entropy_decode(int width, int height, int channels, int levels, int level_chg, int align,
                        const uint8_t *payload, size_t size, void *image_arena);
+/* ric_entropy_encode_hinted: the same payload through the form the device stage uses -- a data-parallel pre-pass
+ * computes per 4x4 block what depends on the band data only (skipped / insignificant / significant, parent
+ * context, non-zero mask, combination index), the serial coder consumes those hints and never writes the bands.
+ * Valid for arenas produced by the encode stage (it relies on the quantiser's parent/child invariant); the
+ * arenas are left untouched.  On the host it exists to check that walker without a GPU. */
+int ric_entropy_encode_hinted(int width, int height, int channels, int levels, int level_chg, int align,
+                              const void *image_arena, uint8_t *out, size_t cap, size_t *size);
 
 /* Plane-at-a-time form of the same stage, the granularity of the reference API: ONE coder object shared by
  * the planes of an image (CMuxCodec, src/lib/muxcodec.h:60-139) and one call per plane (the entropy half of

@@ -26,7 +26,7 @@ EXPORTS = [
     "ric_entropy_encode", "ric_entropy_decode", "ric_compress_u8", "ric_decompress_u8",
     "ric_mux_encoder", "ric_mux_decoder", "ric_mux_code_plane", "ric_mux_decode_plane", "ric_mux_finish",
     "ric_mux_destroy", "ric_entropy_encode_device", "ric_entropy_decode_device",
-    "ric_compress_u8_gpu", "ric_decompress_u8_gpu",
+    "ric_compress_u8_gpu", "ric_decompress_u8_gpu", "ric_entropy_encode_hinted",
 ]
 
 
@@ -90,6 +90,7 @@ def lib():
         L.ric_get_level_times.argtypes = [vp, i, C.POINTER(C.c_float), i]
         L.ric_entropy_encode.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
         L.ric_entropy_decode.argtypes = [i] * 6 + [vp, sz, vp]
+        L.ric_entropy_encode_hinted.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
         L.ric_compress_u8.argtypes = [vp, vp, i, i, vp, sz, vp, i]
         L.ric_entropy_encode_device.argtypes = [vp, vp, i, vp, sz, vp, vp]
         L.ric_entropy_decode_device.argtypes = [vp, vp, sz, vp, i, vp, vp]
@@ -138,17 +139,18 @@ def _ptr(a):
     return a.ctypes.data if isinstance(a, np.ndarray) else int(a)
 
 
-def entropy_encode(width, height, channels, image_arena, levels=5, level_chg=None, align=32, cap=None):
+def entropy_encode(width, height, channels, image_arena, levels=5, level_chg=None, align=32, cap=None, hinted=False):
     """Host entropy stage: one image's quantised band arenas -> .ric payload (bytes after the header).
-    The arenas are consumed (markers cleared in place).  No GPU involved."""
+    The arenas are consumed (markers cleared in place).  No GPU involved.  hinted=True: the pre-pass + hinted
+    walker the device stage uses (arenas untouched)."""
     if level_chg is None:
         level_chg = max(levels - 4, 0)
     if cap is None:
         cap = 2 * width * height * channels + 4096
     out = np.empty(cap, dtype=np.uint8)
     n = C.c_size_t()
-    _check(lib().ric_entropy_encode(width, height, channels, levels, level_chg, align, _ptr(image_arena),
-                                    _ptr(out), cap, C.byref(n)))
+    fn = lib().ric_entropy_encode_hinted if hinted else lib().ric_entropy_encode
+    _check(fn(width, height, channels, levels, level_chg, align, _ptr(image_arena), _ptr(out), cap, C.byref(n)))
     return out[:n.value].copy()
 
 

@@ -895,6 +895,19 @@ int ric_entropy_encode(int width, int height, int channels, int levels, int leve
 	return RIC_OK;
 }
 
+int ric_entropy_encode_hinted(int width, int height, int channels, int levels, int level_chg, int align, const void *image_arena,
+                              uint8_t *out, size_t cap, size_t *size)
+{
+	HostGeom g;
+	int rc = entropy_geom(g, width, height, channels, levels, level_chg, align, "ric_entropy_encode_hinted");
+	if (rc) return rc;
+	if (!image_arena || !out || !size) return set_err(RIC_E_ARG, "ric_entropy_encode_hinted: null");
+	const long n = entropy_encode_image_hinted(g, (const char *)image_arena, out, cap);
+	if (n < 0) return set_err(RIC_E_NOMEM, "ric_entropy_encode_hinted: output buffer too small");
+	*size = (size_t)n;
+	return RIC_OK;
+}
+
 int ric_entropy_decode(int width, int height, int channels, int levels, int level_chg, int align, const uint8_t *payload,
                        size_t size, void *image_arena)
 {

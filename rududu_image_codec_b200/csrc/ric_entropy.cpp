@@ -2,6 +2,8 @@
 // ric_entropy_core.h.  See ric_entropy.h for the reference map.
 #include "ric_entropy.h"
 
+#include <vector>
+
 #include "ric_entropy_core.h"
 
 namespace ric {
@@ -22,6 +24,25 @@ long entropy_encode_image(const HostGeom &g, char *image_arena, uint8_t *out, si
 	for (int i = 0; i < g.channels; i++) {
 		const int plane = g.channels == 3 ? 2 - i : 0;  // Y, Cg, Co
 		walk_plane(io, g, image_arena + (size_t)plane * g.arena_bytes);
+	}
+	uint8_t *end = w.finish();
+	return w.overflow() ? -1 : (long)(end - out);
+}
+
+// The hinted encoder on the host: the pre-pass runs as a plain loop, then the hinted walker.  It exists so
+// that the device path's walker (same source) can be checked without a GPU; the arenas are left untouched.
+long entropy_encode_image_hinted(const HostGeom &g, const char *image_arena, uint8_t *out, size_t cap)
+{
+	std::vector<BlockHint> hints(g.flag_bytes);
+	MuxWriter w(out, cap);
+	WPort io(w, &kTables);
+	for (int i = 0; i < g.channels; i++) {
+		const int plane = g.channels == 3 ? 2 - i : 0;
+		const char *pl = image_arena + (size_t)plane * g.arena_bytes;
+		for (int id = 0; id < 3 * g.nlev; id++)
+			for (int by = 0; by < (g.band[id].dimy + 3) / 4; by++)
+				for (int bx = 0; bx < g.flag_bw[id]; bx++) hints[hint_slot(g, id, bx, by)] = make_hint(g, kTables, pl, id, bx, by);
+		walk_plane_hinted(io, g, const_cast<char *>(pl), hints.data());
 	}
 	uint8_t *end = w.finish();
 	return w.overflow() ? -1 : (long)(end - out);

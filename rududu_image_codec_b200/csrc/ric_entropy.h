@@ -25,6 +25,10 @@ namespace ric {
 // reference's tree<encode> does.  Returns the payload size, or -1 if `cap` bytes were not enough.
 long entropy_encode_image(const HostGeom &g, char *image_arena, uint8_t *out, size_t cap);
 
+// Same payload through the parallel pre-pass + hinted walker (ric_entropy_core.h), the form the device stage uses.
+// Requires arenas that come from the encode stage; leaves them untouched.
+long entropy_encode_image_hinted(const HostGeom &g, const char *image_arena, uint8_t *out, size_t cap);
+
 // Decode one image's payload into signed quantised band arenas (what the decode stage consumes).
 // `payload` need not be padded.  Returns 0, or -1 on a truncated / over-long stream.
 int entropy_decode_image(const HostGeom &g, const uint8_t *payload, size_t size, char *image_arena);

@@ -770,5 +770,154 @@ RIC_HD void walk_plane(Port &io, const HostGeom &g, char *plane)
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Encoding with a parallel pre-pass ("block hints").
+//
+// Everything the band walker derives from the band DATA alone -- whether a block is skipped because its
+// parent block is insignificant, whether it is insignificant itself, its parent-magnitude context, which of
+// its samples are non-zero and the index of that combination -- does not depend on the coder's adaptive state,
+// so it can be computed for all blocks at once (one thread per block on the device) and leave the serial
+// coder with the models, the range coder and the bit fields.  The hinted walker reads the bands but never
+// writes them (the in-place marker bookkeeping of walk_band is what the hints replace).
+//
+// The skip rule relies on the quantiser's own invariant (buildTree accumulates children into parents,
+// bandcodec.cpp:291-296): a block under an insignificant full parent block is insignificant itself, so
+// "parent cell marked at walk time" == "the parent block is full and carries the marker".  Arenas from the
+// encode stage always satisfy it; for arbitrary arenas use the plain walker.
+// ---------------------------------------------------------------------------------------------
+struct BlockHint {
+	uint32_t a;  // bits 0-15 non-zero mask (scan order), 16-19 parent context, 20-21 state
+	uint32_t idx;  // index of the combination (flipped when k > 8), ready for the truncated code
+};
+enum : uint32_t { kHintDead = 0, kHintInsig = 1, kHintSig = 2 };
+
+// Hint slot of block (bx, by) of band `id`: the block-flag indexing of HostGeom (one slot per 4x4 block).
+RIC_HD inline size_t hint_slot(const HostGeom &g, int id, int bx, int by) { return (size_t)g.flag_off[id] + (size_t)by * g.flag_bw[id] + bx; }
+
+template <class C, class P>
+RIC_HD inline BlockHint make_hint_t(const HostGeom &g, const Tables &T, const char *plane, int id, int bx, int by)
+{
+	const ric_band_info &b = g.band[id];
+	const C *blk = (const C *)(plane + b.offset) + (size_t)(4 * by) * b.stride + 4 * bx;
+	const int w = b.dimx - 4 * bx < 4 ? b.dimx - 4 * bx : 4, h = b.dimy - 4 * by < 4 ? b.dimy - 4 * by : 4;
+	const bool full = w == 4 && h == 4;
+	BlockHint r{0, 0};
+	uint32_t state = blk[0] == kMarker ? kHintInsig : kHintSig, ctx = 15;
+	const int lev = id / 3;
+	if (full && lev < g.nlev - 1) {
+		const ric_band_info &pb = g.band[id + 3];
+		const P *par = (const P *)(plane + pb.offset);
+		const int pbx = bx >> 1, pby = by >> 1;
+		const bool pfull = pb.dimx - 4 * pbx >= 4 && pb.dimy - 4 * pby >= 4;
+		if (pfull && par[(size_t)(4 * pby) * pb.stride + 4 * pbx] == kMarker) state = kHintDead;
+		else {
+			int c = parent_ctx<true, P>(par + (size_t)(2 * by) * pb.stride + 2 * bx, pb.stride);
+			ctx = (uint32_t)(c > 15 ? 15 : c);
+		}
+	}
+	uint32_t mask = 0;
+	if (full && state == kHintSig) {
+		mask = nonzero_mask(blk, b.stride);
+		const unsigned k = (unsigned)count_ones(mask);
+		if (k != 0 && k != 16) {
+			uint32_t m = k > 8 ? mask ^ 0xFFFFu : mask, idx = 0;
+			for (unsigned rr = 0; m; rr++) {
+				const unsigned i = 31 - (unsigned)count_lz(m);
+				idx += T.choose[rr][15 - i];
+				m ^= 1u << i;
+			}
+			r.idx = idx;
+		}
+	}
+	r.a = mask | ctx << 16 | state << 20;
+	return r;
+}
+
+RIC_HD inline BlockHint make_hint(const HostGeom &g, const Tables &T, const char *plane, int id, int bx, int by)
+{
+	const int lev = id / 3;
+	const bool ci = g.lev_int[lev] != 0, pi = lev < g.nlev - 1 ? g.lev_int[lev + 1] != 0 : ci;
+	if (ci) return make_hint_t<int32_t, int32_t>(g, T, plane, id, bx, by);
+	if (pi) return make_hint_t<int16_t, int32_t>(g, T, plane, id, bx, by);
+	return make_hint_t<int16_t, int16_t>(g, T, plane, id, bx, by);
+}
+
+template <bool FINE, class C>
+RIC_HD void walk_band_hinted(WPort &io, const C *base, const ric_band_info &b, const BlockHint *hints, int bw)
+{
+	const Tables &T = *io.T;
+	uint16_t kmean[16];
+	for (int i = 0; i < 16; i++) kmean[i] = T.kmean_init[i];
+	GeomModel geo(T.band_init, T.geo_bound);
+	BitModel tree_bit(T.bit_lim), edge_bit(T.bit_lim);
+	const int nfull = b.dimx >> 2, rem = b.dimx & 3, nblk = nfull + (rem ? 1 : 0);
+	for (int y = 0, by = 0; y < b.dimy; y += 4, by++) {
+		const int h = b.dimy - y < 4 ? b.dimy - y : 4;
+		const C *row = base + (size_t)y * b.stride;
+		const BlockHint *hrow = hints + (size_t)by * bw;
+		const bool backwards = (y & 4) != 0;
+		for (int t = 0; t < nblk; t++) {
+			const int bx = backwards ? nblk - 1 - t : t;
+			const BlockHint hint = hrow[bx];
+			const uint32_t state = (hint.a >> 20) & 3;
+			const int w = bx < nfull ? 4 : rem;
+			C *blk = const_cast<C *>(row) + 4 * bx;  // code_block's writing side only reads
+			if (w == 4 && h == 4) {
+				if (state == kHintDead) continue;
+				const unsigned ctx = (hint.a >> 16) & 15;
+				if (tree_bit.code(io, state == kHintInsig, ctx)) continue;
+				const int table = (kmean[ctx] + (1 << 9)) >> 10;
+				const uint32_t mask = hint.a & 0xFFFFu;
+				const unsigned k = (unsigned)count_ones(mask);
+				const CountCode &c = FINE ? T.fine[table] : T.low[table];
+				const unsigned s = FINE ? k - 1 : k;
+				io.bits(c.code[s], c.len[s]);
+				if (k != 0) {
+					if (k != 16) {
+						const unsigned kk = k > 8 ? 16 - k : k;
+						const unsigned len = T.enum_len[16][kk];
+						const uint32_t nshort = T.enum_short[16][kk];
+						if (hint.idx < nshort) io.bits(hint.idx, len - 1); else io.bits(hint.idx + nshort, len);
+					}
+					for (uint32_t m = mask; m; m &= m - 1) {
+						const unsigned i = (unsigned)count_tz(m);
+						const C v = blk[(i >> 2) * b.stride + (i & 3)];
+						const uint32_t u = sizeof(C) == 2 ? (uint16_t)v : (uint32_t)v;
+						geo.code(io, (u >> 1) - 1, k - 1);
+						io.bits(u & 1, 1);
+					}
+				}
+				const unsigned kk2 = k - (FINE ? 1 : 0);
+				kmean[ctx] = (uint16_t)(kmean[ctx] + (kk2 << 7) - (kmean[ctx] >> 3));
+			} else {
+				if (edge_bit.code(io, state == kHintInsig, 0)) continue;
+				code_block<FINE>(io, geo, blk, b.stride, w, h, 0);
+			}
+		}
+	}
+}
+
+// One plane, luma-first order handled by the caller.  `hints`: the plane's hint slots (g.flag_bytes of them).
+RIC_HD inline void walk_plane_hinted(WPort &io, const HostGeom &g, char *plane, const BlockHint *hints)
+{
+	const int n = g.nlev, ll = 3 * n;
+	if (g.band[ll].is_int) walk_ll(io, band_ref<int32_t>(g, plane, ll));
+	else walk_ll(io, band_ref<int16_t>(g, plane, ll));
+	for (int lev = n - 1; lev >= 0; lev--)
+		for (int o = 0; o < 3; o++) {
+			const int id = 3 * lev + 2 - o;  // V, H, D
+			const ric_band_info &b = g.band[id];
+			const BlockHint *h = hints + g.flag_off[id];
+			if (g.lev_int[lev]) {
+				const int32_t *p = (const int32_t *)(plane + b.offset);
+				if (lev == 0) walk_band_hinted<true>(io, p, b, h, g.flag_bw[id]); else walk_band_hinted<false>(io, p, b, h, g.flag_bw[id]);
+			} else {
+				const int16_t *p = (const int16_t *)(plane + b.offset);
+				if (lev == 0) walk_band_hinted<true>(io, p, b, h, g.flag_bw[id]); else walk_band_hinted<false>(io, p, b, h, g.flag_bw[id]);
+			}
+		}
+}
+
+
 }  // namespace ent
 }  // namespace ric

@@ -109,6 +109,7 @@ def test_golden_payloads_from_oracle_arenas(golden):
         assert crc(arenas) == k["enc_arena_crc"]
         payload = capi.entropy_encode(w, h, ch, arenas.copy(), levels=k["levels"])
         assert (len(payload), crc(payload)) == (k["payload_bytes"], k["payload_crc"]), k
+        assert capi.entropy_encode(w, h, ch, arenas, levels=k["levels"], hinted=True).tobytes() == payload.tobytes(), k
         back = np.full(arenas.size, 0x3C, dtype=np.uint8)
         capi.entropy_decode(w, h, ch, payload, back, levels=k["levels"])
         assert crc(back) == k["dec_arena_crc"], k
@@ -199,6 +200,9 @@ def test_random_geometries_match_reference():
         arenas = o.encode_image(img, q)
         got = capi.entropy_encode(w, h, ch, arenas.copy(), levels=levels, level_chg=lc, cap=4 * w * h * ch + 4096)
         assert got.tobytes() == bytes(want), (w, h, ch, q, levels, lc, trans, kind)
+        keep = arenas.copy()
+        hinted = capi.entropy_encode(w, h, ch, arenas, levels=levels, level_chg=lc, cap=4 * w * h * ch + 4096, hinted=True)
+        assert hinted.tobytes() == bytes(want) and np.array_equal(arenas, keep), (w, h, ch, q, levels, lc, trans, kind)
         back = np.full(arenas.size, 0x11, dtype=np.uint8)
         capi.entropy_decode(w, h, ch, got, back, levels=levels, level_chg=lc)
         for p in range(ch):
