@@ -192,8 +192,11 @@ int ric_mux_destroy(ric_mux *mux);
 /* The same stage ON THE DEVICE, for large batches: one image per warp, the identical coder source.  The
  * stream of an image is serial, so this only pays when thousands of images are resident (BASELINE configs[3]);
  * what it buys is that the band arenas never cross PCIe -- only the finished payloads do.
- * d_arenas: n image arenas in device memory, as ric_encode_u8_device wrote them (consumed) / as
- * ric_decode_u8_device reads them (written).  d_out / d_payloads: n slots of `stride` bytes; d_sizes: n
+ * d_arenas: n image arenas in device memory, as ric_encode_u8_device wrote them / as ric_decode_u8_device
+ * reads them (written).  The encoder runs a data-parallel pre-pass over all 4x4 blocks (skipped / insignificant /
+ * significant, parent context, non-zero mask, combination index) and a serial coder per image that consumes
+ * those hints; it relies on the encode stage's parent/child invariant, so feed it encode-stage arenas only
+ * (environment variable RIC_ENTROPY_PLAIN=1 selects the plain walker, which accepts any arenas and consumes them).  d_out / d_payloads: n slots of `stride` bytes; d_sizes: n
  * payload lengths (encode writes -1 where `stride` was too small).  Asynchronous on `stream`. */
 int ric_entropy_encode_device(ric_ctx *ctx, void *d_arenas, int n, uint8_t *d_out, size_t stride, long long *d_sizes,
                               void *stream);

@@ -55,6 +55,7 @@ struct ric_ctx {
 	HostGeom *d_geom;       // device copies for the GPU entropy stage (allocated on first use)
 	void *d_tables;         // ent::Tables, a POD block
 	int *d_bad;
+	void *d_hints;          // block hints of the device entropy encoder: [max_batch][channels][flag_bytes] x 8 bytes
 	uint8_t *d_payload;     // [max_batch][payload_stride] device-side .ric payload slots
 	size_t payload_stride;
 	long long *d_psizes, *h_psizes;  // payload lengths, device and pinned host
@@ -267,6 +268,7 @@ int ric_destroy(ric_ctx *c)
 	cudaFree(c->d_geom);
 	cudaFree(c->d_tables);
 	cudaFree(c->d_bad);
+	cudaFree(c->d_hints);
 	cudaFree(c->d_payload);
 	cudaFree(c->d_psizes);
 	if (c->h_psizes) cudaFreeHost(c->h_psizes);
@@ -993,6 +995,8 @@ static int need_entropy_tables(ric_ctx *c)
 	CK(cudaMemcpy(c->d_geom, &c->g, sizeof(HostGeom), cudaMemcpyHostToDevice));
 	CK(cudaMalloc(&c->d_bad, sizeof(int)));
 	CK(cudaMemset(c->d_bad, 0, sizeof(int)));
+	cudaError_t e = cudaMalloc(&c->d_hints, hint_bytes(c->g, c->max_batch));
+	if (e != cudaSuccess) return set_err(RIC_E_NOMEM, "cudaMalloc(block hints): %s", cudaGetErrorString(e));
 	return RIC_OK;
 }
 
@@ -1002,8 +1006,13 @@ int ric_entropy_encode_device(ric_ctx *c, void *d_arenas, int n, uint8_t *d_out,
 	CK(cudaSetDevice(c->device));
 	int rc = need_entropy_tables(c);
 	if (rc) return rc;
-	CK(launch_entropy_encode(c->d_geom, c->d_tables, (char *)d_arenas, (size_t)c->g.channels * c->g.arena_bytes, d_out, stride, d_sizes, n,
-	                         (cudaStream_t)stream));
+	if (n > c->max_batch) return set_err(RIC_E_ARG, "ric_entropy_encode_device: n > max_batch");
+	if (getenv("RIC_ENTROPY_PLAIN"))  // the plain walker (in-place marker bookkeeping, no pre-pass), for comparison
+		CK(launch_entropy_encode(c->d_geom, c->d_tables, (char *)d_arenas, (size_t)c->g.channels * c->g.arena_bytes, d_out, stride, d_sizes, n,
+		                         (cudaStream_t)stream));
+	else
+		CK(launch_entropy_encode_hinted(c->d_geom, c->g, c->d_tables, (char *)d_arenas, (size_t)c->g.channels * c->g.arena_bytes, c->d_hints,
+		                                d_out, stride, d_sizes, n, (cudaStream_t)stream));
 	return RIC_OK;
 }
 
@@ -1100,7 +1109,8 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 		CK(cudaEventRecord(c->ent_ev[i], c->pipe[i]));
 		CK(cudaStreamWaitEvent(es, c->ent_ev[i], 0));
 	}
-	CK(launch_entropy_encode(c->d_geom, c->d_tables, c->d_arena, img_ar, c->d_payload, c->payload_stride, c->d_psizes, n, es));
+	CK(launch_entropy_encode_hinted(c->d_geom, c->g, c->d_tables, c->d_arena, img_ar, c->d_hints, c->d_payload, c->payload_stride, c->d_psizes,
+	                                n, es));
 	CK(cudaMemcpyAsync(c->h_psizes, c->d_psizes, sizeof(long long) * n, cudaMemcpyDeviceToHost, es));
 	c->launches = total + 1;
 	stamp("enqueued", 0);

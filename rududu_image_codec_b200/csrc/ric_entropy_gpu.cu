@@ -45,6 +45,59 @@ __global__ void __launch_bounds__(64) entropy_decode_kernel(const HostGeom *gp, 
 	if (r.overrun()) atomicExch(bad, 1);
 }
 
+
+// ---- encode with the parallel pre-pass (block hints, ric_entropy_core.h) ---------------------------------
+// hint_kernel: one thread per 4x4 block of every D/H/V band of every plane of every image.
+__global__ void __launch_bounds__(256) hint_kernel(const HostGeom *gp, const ent::Tables *T, const char *arenas, size_t img_ar,
+                                                   ent::BlockHint *hints, int nplanes_total)
+{
+	const HostGeom &g = *gp;
+	const long long slots = (long long)g.flag_bytes;
+	const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (gid >= slots * nplanes_total) return;
+	const int pl = (int)(gid / slots);
+	const int slot = (int)(gid % slots);
+	// which band / block is this slot?  (bands are laid out back to back, each padded to 16 slots)
+	int id = 0;
+	while (id + 1 < 3 * g.nlev && slot >= g.flag_off[id + 1]) id++;
+	const int rel = slot - g.flag_off[id], bw = g.flag_bw[id];
+	const int by = rel / bw, bx = rel % bw;
+	if (by >= (g.band[id].dimy + 3) / 4) return;  // padding slot
+	const int img = pl / g.channels, plane = pl % g.channels;
+	hints[gid] = ent::make_hint(g, *T, arenas + (size_t)img * img_ar + (size_t)plane * g.arena_bytes, id, bx, by);
+}
+
+__global__ void __launch_bounds__(64) entropy_encode_hinted_kernel(const HostGeom *gp, const ent::Tables *T, char *arenas, size_t img_ar,
+                                                                   const ent::BlockHint *hints, uint8_t *out, size_t stride,
+                                                                   long long *sizes, int n)
+{
+	const int img = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	if (img >= n || (threadIdx.x & 31)) return;
+	const HostGeom &g = *gp;
+	uint8_t *o = out + (size_t)img * stride;
+	ent::MuxWriter w(o, stride);
+	ent::WPort io(w, T);
+	for (int i = 0; i < g.channels; i++) {
+		const int plane = g.channels == 3 ? 2 - i : 0;
+		ent::walk_plane_hinted(io, g, arenas + (size_t)img * img_ar + (size_t)plane * g.arena_bytes,
+		                       hints + ((size_t)img * g.channels + plane) * g.flag_bytes);
+	}
+	uint8_t *end = w.finish();
+	sizes[img] = w.overflow() ? -1 : (long long)(end - o);
+}
+
+cudaError_t launch_entropy_encode_hinted(const HostGeom *g, const HostGeom &hg, const void *tables, char *arenas, size_t img_ar, void *hints,
+                                         uint8_t *out, size_t stride, long long *sizes, int n, cudaStream_t st)
+{
+	const long long total = (long long)hg.flag_bytes * hg.channels * n;
+	hint_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, (const ent::Tables *)tables, arenas, img_ar, (ent::BlockHint *)hints, hg.channels * n);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	entropy_encode_hinted_kernel<<<(n + 1) / 2, 64, 0, st>>>(g, (const ent::Tables *)tables, arenas, img_ar, (const ent::BlockHint *)hints, out, stride,
+	                                                         sizes, n);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_entropy_encode(const HostGeom *g, const void *tables, char *arenas, size_t img_ar, uint8_t *out, size_t stride,
                                   long long *sizes, int n, cudaStream_t st)
 {
