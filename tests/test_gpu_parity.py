@@ -544,3 +544,31 @@ def test_ric_file_many_workers():
         for _ in range(15):
             assert c.compress_u8(imgs, 9, threads=16) == first
         assert np.array_equal(c.decompress_u8(first, threads=16), c.decompress_u8(first, entropy_on_device=True))
+
+
+def test_entropy_stage_on_device_plain_walker(monkeypatch):
+    """RIC_ENTROPY_PLAIN=1 selects the plain device walker (no pre-pass; consumes the arenas like the host
+    stage): same payloads as the default hinted encoder."""
+    import torch
+    w, h, ch, q, n = 320, 200, 3, 9, 3
+    imgs = np.stack([synth_image(60 + i, w, h, ch) for i in range(n)])
+    stride = w * h * ch * 2
+    with capi.Context(w, h, ch, 5, max_batch=n) as c:
+        st = torch.cuda.current_stream().cuda_stream
+        pitch = (w + 7) & ~7
+        src = torch.zeros((n, ch, h, pitch), dtype=torch.uint8, device="cuda")
+        src[..., :w] = torch.from_numpy(imgs).cuda()
+        ar = torch.zeros(n * c.image_arena_bytes, dtype=torch.uint8, device="cuda")
+        outs = []
+        for plain in (False, True):
+            if plain:
+                monkeypatch.setenv("RIC_ENTROPY_PLAIN", "1")
+            c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
+            before = ar.clone()
+            out = torch.zeros(n * stride, dtype=torch.uint8, device="cuda")
+            sizes = torch.zeros(n, dtype=torch.int64, device="cuda")
+            c.entropy_encode_device(ar.data_ptr(), n, out.data_ptr(), stride, sizes.data_ptr(), st)
+            torch.cuda.synchronize()
+            assert torch.equal(ar, before) != plain  # the hinted coder leaves the arenas alone, the plain one consumes them
+            outs.append((out.cpu().numpy(), sizes.cpu().numpy()))
+        assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
