@@ -21,7 +21,7 @@ EXPORTS = [
     "ric_create", "ric_destroy", "ric_get_info", "ric_get_band", "ric_last_error", "ric_quants",
     "ric_plane_quant", "ric_encode_u8", "ric_decode_u8", "ric_encode_u8_device", "ric_decode_u8_device",
     "ric_last_launch_count", "ric_transform", "ric_quant", "ric_tsuq", "ric_tsuqi", "ric_transform_inv",
-    "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times",
+    "ric_host_alloc", "ric_host_free", "ric_set_profiling", "ric_get_level_times", "ric_get_path_stats",
     "ric_encode_u8_stream", "ric_decode_u8_stream", "ric_sync", "ric_header_write", "ric_header_parse",
     "ric_entropy_encode", "ric_entropy_decode", "ric_compress_u8", "ric_decompress_u8",
     "ric_mux_encoder", "ric_mux_decoder", "ric_mux_code_plane", "ric_mux_decode_plane", "ric_mux_finish",
@@ -88,6 +88,7 @@ def lib():
         L.ric_header_write.argtypes = [vp, i, i, i, i, i]
         L.ric_header_parse.argtypes = [vp] + [C.POINTER(i)] * 5
         L.ric_get_level_times.argtypes = [vp, i, C.POINTER(C.c_float), i]
+        L.ric_get_path_stats.argtypes = [vp, C.POINTER(C.c_ulonglong), i]
         L.ric_entropy_encode.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
         L.ric_entropy_decode.argtypes = [i] * 6 + [vp, sz, vp]
         L.ric_entropy_encode_hinted.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
@@ -321,6 +322,12 @@ class Context:
 
     def set_profiling(self, on=True):
         _check(self.L.ric_set_profiling(self.h, int(on)))
+
+    def path_stats(self):
+        """Packed-kernel path counters since the last call (profiling must be on): [fwd iterations, fwd scalar, inv iterations, inv scalar]."""
+        buf = (C.c_ulonglong * 4)()
+        _check(self.L.ric_get_path_stats(self.h, buf, 4))
+        return [int(v) for v in buf]
 
     def level_times(self, direction):
         """Per-launch durations (ms) of the last encode (0) / decode (1) *_device call."""

@@ -19,6 +19,7 @@
 #include "ric_entropy.h"
 #include "ric_entropy_gpu.h"
 #include "ric_fwd.cuh"
+#include "ric_fwd0.cuh"
 #include "ric_host.h"
 #include "ric_inv.cuh"
 
@@ -69,6 +70,7 @@ struct ric_ctx {
 	int ll_pitch[RIC_MAX_LEVELS];
 	int ll_es[RIC_MAX_LEVELS];
 	unsigned *d_count;
+	unsigned long long *d_stats;         // path statistics of the packed kernels (filled while profiling is on)
 	unsigned long long *d_jobctr;        // job counters of the persistent kernels: [4 stream sets][2 directions][levels]
 	int cset;                            // counter set in use (0-2: internal pipeline streams, 3: caller's stream)
 	int launches;
@@ -76,6 +78,7 @@ struct ric_ctx {
 	cudaEvent_t ev[2][RIC_MAX_LEVELS + 1];  // [direction][launch boundary]
 	int ev_n[2];
 	int target_warps;
+	int use_fwd0;                        // packed level-0 forward kernel (RIC_FWD0=0 switches back to the scalar one)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -191,17 +194,31 @@ __global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int 
 
 // ---------------------------------------------------------------------------------------------
 
+static int getenv(const char *name, int dflt)
+{
+	const char *v = ::getenv(name);
+	return v ? atoi(v) : dflt;
+}
+
 static void fill_qb(QuantBand &q, int Quant, int lambda, float weight, int is_int)
 {
 	HostQuantBand hq;
 	make_quant_band(hq, Quant, lambda, weight, is_int);
 	q.Q = hq.Q; q.iQ = hq.iQ; q.T = hq.T; q.Te = hq.Te;
 	q.fast = hq.Q >= 1 && hq.Q <= (is_int ? 32767 : 16383);
-	for (int i = 0; i < 32; i++) q.kthr[i] = 0x7fffffff;
+	for (int i = 0; i < 32; i++) q.kthr[i] = q.kt16[i] = 0x7fffffff;
 	for (int i = 0; i < 16; i++) {
 		q.thr[i] = hq.thr[i];
 		if (q.fast) q.kthr[i] = hq.thr[i] << 4;
 	}
+	// packed form (short levels only): 16-bit keys hold f - 2T in 11 bits, the quantised value 2q|sign in 15
+	q.pk = !is_int && q.fast && hq.Q >= 4 && !(hq.thr[0] & 1) && getenv("RIC_QUANT_PK", 1);
+	for (int i = 0; i < 16 && q.pk; i++) {
+		const int d = hq.thr[i] - 2 * hq.T;
+		if (d < 0 || d > 2046) q.pk = 0;
+		else q.kt16[i] = 0x8000 | (d << 4);
+	}
+	q.h0 = std::max(hq.thr[0] >> 1, hq.T + 1);
 }
 
 static BandRef band_ref(const HostGeom &g, int id)
@@ -279,6 +296,7 @@ int ric_destroy(ric_ctx *c)
 	cudaFree(c->d_flags);
 	cudaFree(c->d_plane);
 	cudaFree(c->d_count);
+	cudaFree(c->d_stats);
 	cudaFree(c->d_jobctr);
 	for (int d = 0; d < 2; d++)
 		for (int i = 0; i <= RIC_MAX_LEVELS; i++)
@@ -315,6 +333,8 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	c->sm_count = prop.multiProcessorCount;
 	const char *tw = getenv("RIC_TARGET_WARPS");
 	c->target_warps = tw ? atoi(tw) : 0;  // override of the concurrent-job count used by choose_seg_rows
+	const char *f0 = getenv("RIC_FWD0");
+	c->use_fwd0 = f0 ? atoi(f0) : 1;
 #define CKD(call)                                                                    \
 	do {                                                                             \
 		cudaError_t e_ = (call);                                                     \
@@ -325,6 +345,8 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 		}                                                                            \
 	} while (0)
 	CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CKD(cudaFuncSetAttribute(fwd0_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f0_smem_bytes<3>()));
+	CKD(cudaFuncSetAttribute(fwd0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f0_smem_bytes<1>()));
 	for (int i = 0; i < 3; i++) CKD(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
 	const size_t nb = (size_t)max_batch, ch = (size_t)channels;
 	c->src_pitch = ((size_t)width + 7) & ~(size_t)7;  // roundup8(w): dense rows (one contiguous copy) when w % 8 == 0
@@ -343,6 +365,8 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 		CKD(cudaMemset(c->d_ll[i], 0, bytes));
 	}
 	CKD(cudaMalloc(&c->d_count, sizeof(unsigned)));
+	CKD(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
+	CKD(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
 	CKD(cudaMalloc(&c->d_jobctr, 4 * 2 * RIC_MAX_LEVELS * sizeof(unsigned long long)));
 	c->cset = 3;
 	for (int d = 0; d < 2; d++)
@@ -390,6 +414,16 @@ int ric_get_level_times(ric_ctx *c, int direction, float *ms, int cap)
 	CK(cudaEventSynchronize(c->ev[direction][n]));
 	for (int i = 0; i < n; i++) CK(cudaEventElapsedTime(&ms[i], c->ev[direction][i], c->ev[direction][i + 1]));
 	return n;
+}
+
+int ric_get_path_stats(ric_ctx *c, unsigned long long *out, int n)
+{
+	if (!c || !out || n < 1 || n > 8) return set_err(RIC_E_ARG, "ric_get_path_stats: bad argument");
+	CK(cudaSetDevice(c->device));
+	CK(cudaDeviceSynchronize());
+	CK(cudaMemcpy(out, c->d_stats, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	CK(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+	return RIC_OK;
 }
 
 int ric_header_write(uint8_t *out, int width, int height, int q, int color, int trans)
@@ -499,14 +533,29 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 				make_tsuq(Quant[p], 0.5f, g.band[3 * g.nlev].weight, g.lev_int[g.nlev - 1], &P.llQ[cls], &P.lliQ[cls], &P.llT[cls]);
 			}
 		}
-		fwd_fn fn = pick_fwd(sh, g.trans, src);
-		if (!fn) return set_err(RIC_E_UNSUPPORTED, "forward: unsupported level type combination");
-		const long long njobs = (long long)P.nstrips * P.nsegs * nplanes * n;
-		if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "forward: batch too large for one launch");
-		const int wpb = fwd_warps(sh);
 		P.counter = ctr + lv;
-		const unsigned grid = (unsigned)std::min<long long>((njobs + wpb - 1) / wpb, (long long)c->sm_count * 4);
-		fn<<<grid, wpb * 32, 0, st>>>(P);
+		P.stats = c->profiling ? c->d_stats : nullptr;
+		// level 0 from 8-bit pixels: the packed kernel (ric_fwd0.cuh), one warp job = all planes of a strip segment
+		const bool packed0 = c->use_fwd0 && lv == 0 && sh && !last && shift && g.trans == RIC_CDF97 &&
+		                     ((src == SRC_U8_RGB && nplanes == 3) || (src == SRC_U8_GRAY && nplanes == 1));
+		if (packed0) {
+			const int occ = nplanes == 3 ? 3 : 4;
+			P.seg_rows = choose_seg_rows(c, P.w, P.h, (long long)n, F0_WARPS * occ);
+			P.nsegs = (P.h + P.seg_rows - 1) / P.seg_rows;
+			const long long njobs = (long long)P.nstrips * P.nsegs * n;
+			if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "forward: batch too large for one launch");
+			const unsigned grid = (unsigned)std::min<long long>((njobs + F0_WARPS - 1) / F0_WARPS, (long long)c->sm_count * occ);
+			if (nplanes == 3) fwd0_kernel<3><<<grid, F0_WARPS * 32, f0_smem_bytes<3>(), st>>>(P);
+			else fwd0_kernel<1><<<grid, F0_WARPS * 32, f0_smem_bytes<1>(), st>>>(P);
+		} else {
+			fwd_fn fn = pick_fwd(sh, g.trans, src);
+			if (!fn) return set_err(RIC_E_UNSUPPORTED, "forward: unsupported level type combination");
+			const long long njobs = (long long)P.nstrips * P.nsegs * nplanes * n;
+			if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "forward: batch too large for one launch");
+			const int wpb = fwd_warps(sh);
+			const unsigned grid = (unsigned)std::min<long long>((njobs + wpb - 1) / wpb, (long long)c->sm_count * 4);
+			fn<<<grid, wpb * 32, 0, st>>>(P);
+		}
 		CK(cudaGetLastError());
 		c->launches++;
 		if (c->profiling) { CK(cudaEventRecord(c->ev[0][c->launches], st)); c->ev_n[0] = c->launches; }

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ric_quant_pk.cuh"
+
 namespace ric {
 
 enum { T97 = 0, T53 = 1, THAAR = 2 };  // Haar: S1/S2 (U2/U1) only, pairs without neighbours; even sizes only
@@ -267,36 +269,6 @@ RIC_VSTEP(vU3, (iU3<SH, TRANS>(x[k], l[k], r[k])), (iU3_edge<SH, TRANS>(x[k], r[
 RIC_VSTEP(vU2, (iU2<SH, TRANS>(x[k], l[k], r[k])), (x[k]), (iU2_last<SH, TRANS>(x[k], l[k])))
 RIC_VSTEP(vU1, (iU1<SH, TRANS>(x[k], l[k], r[k])), (iU1_first<SH, TRANS>(x[k], r[k])), (iU1_last<SH, TRANS>(x[k], l[k])))
 #undef RIC_VSTEP
-
-// ---- encode quantiser (CBandCodec::tsuqBlock, bandcodec.cpp:159-237) ----------------------------
-// Host-computed scalars of one band (buildTree :243-247, makeThres :149-157).
-struct QuantBand {
-	int Q, iQ, T, Te;  // T = Q>>1 (full blocks), Te = (Q+((Q-(Q>>2))>>1))>>1 (partial blocks)
-	int thr[16];
-	int fast;          // 1 <= Q <= 16383: every candidate / threshold is a non-negative int16, so signed and
-	                   // unsigned views agree and the rank thresholds can be compared in the key domain
-	int kthr[32];      // fast: thr[n] << 4 (n < 16), INT_MAX beyond
-};
-
-template <bool SH>
-__device__ __forceinline__ unsigned uview(int v) { return SH ? (unsigned)(v & 0xFFFF) : (unsigned)v; }
-
-// Batcher odd-even merge sort of 16 keys, descending: 63 compare-exchanges written out so that the
-// keys provably stay in registers (a rolled network would index them dynamically -> local memory).
-__device__ __forceinline__ void sort16_desc(int (&s)[16])
-{
-#define RIC_CE(i, j) { const int a_ = s[i], b_ = s[j]; s[i] = max(a_, b_); s[j] = min(a_, b_); }
-	RIC_CE(0, 1) RIC_CE(2, 3) RIC_CE(4, 5) RIC_CE(6, 7) RIC_CE(8, 9) RIC_CE(10, 11) RIC_CE(12, 13)
-	RIC_CE(14, 15) RIC_CE(0, 2) RIC_CE(1, 3) RIC_CE(4, 6) RIC_CE(5, 7) RIC_CE(8, 10) RIC_CE(9, 11)
-	RIC_CE(12, 14) RIC_CE(13, 15) RIC_CE(1, 2) RIC_CE(5, 6) RIC_CE(9, 10) RIC_CE(13, 14) RIC_CE(0, 4)
-	RIC_CE(1, 5) RIC_CE(2, 6) RIC_CE(3, 7) RIC_CE(8, 12) RIC_CE(9, 13) RIC_CE(10, 14) RIC_CE(11, 15)
-	RIC_CE(2, 4) RIC_CE(3, 5) RIC_CE(10, 12) RIC_CE(11, 13) RIC_CE(1, 2) RIC_CE(3, 4) RIC_CE(5, 6)
-	RIC_CE(9, 10) RIC_CE(11, 12) RIC_CE(13, 14) RIC_CE(0, 8) RIC_CE(1, 9) RIC_CE(2, 10) RIC_CE(3, 11)
-	RIC_CE(4, 12) RIC_CE(5, 13) RIC_CE(6, 14) RIC_CE(7, 15) RIC_CE(4, 8) RIC_CE(5, 9) RIC_CE(6, 10)
-	RIC_CE(7, 11) RIC_CE(2, 4) RIC_CE(3, 5) RIC_CE(6, 8) RIC_CE(7, 9) RIC_CE(10, 12) RIC_CE(11, 13)
-	RIC_CE(1, 2) RIC_CE(3, 4) RIC_CE(5, 6) RIC_CE(7, 8) RIC_CE(9, 10) RIC_CE(11, 12) RIC_CE(13, 14)
-#undef RIC_CE
-}
 
 // Quantise one 4x4 block held in registers (c[4*row+col], proper C values), in place, returning
 // the number of non-zero outputs.  bw/bh: valid columns/rows (4,4 = full block -> rank-threshold

@@ -312,6 +312,10 @@ public:
 		uint32_t t = 3u << (nacc_ - 2);
 		while ((~acc_ & t) != t) {
 			l++;
+			// a valid code is at most ~28 bits long (values are folded 16/32-bit samples); a stream
+			// without two consecutive zero bits (0xFF.., 0x55..) would otherwise run the length past the
+			// accumulator and index the 32-entry tables far out of bounds
+			if (l > 32) { past_ += 1000; nacc_ = 0; return 0; }
 			if (l > nacc_) { fill(l); t <<= 8; }
 			t >>= 1;
 		}
@@ -475,7 +479,8 @@ public:
 	RIC_HD inline uint32_t code(Port &io, uint32_t sym, unsigned ctx)
 	{
 		const unsigned st = state_[ctx];
-		const unsigned k = st > 9 ? st - 9 : 0, s = st < 9 ? 10 - st : 1, rate = 3 + s;
+		// (k <= 24: a corrupt stream can walk the state up without bound; valid ones never come near)
+		const unsigned k = st > 9 ? (st - 9 < 24 ? st - 9 : 24) : 0, s = st < 9 ? 10 - st : 1, rate = 3 + s;
 		const uint32_t p = prob_[ctx];
 		uint32_t pr = p, hi = Port::writing ? sym >> k : 0, n = 0;
 		if (Port::writing) {
@@ -489,7 +494,7 @@ public:
 		pr += (kProbOne - pr) >> rate;
 		prob_[ctx] = (uint16_t)pr;
 		if ((uint16_t)(pr - bound(s - 1)) > bound(s) - bound(s - 1)) {
-			if (pr < bound(s - 1)) state_[ctx]++;
+			if (pr < bound(s - 1)) { if (state_[ctx] < 40) state_[ctx]++; }
 			else if (state_[ctx] > 0) state_[ctx]--;
 			if (state_[ctx] >= 9) prob_[ctx] = (uint16_t)kProbHalf;
 		}

@@ -60,6 +60,7 @@ struct FwdParams {
 	QuantBand qb[2][3];        // [class][orientation]
 	int llQ[2], lliQ[2], llT[2];  // LL TSUQ scalars per class
 	unsigned long long *counter;  // dynamic job fetch (zeroed before the launch)
+	unsigned long long *stats;    // optional (profiling): [0] packed-kernel plane iterations, [1] of those on the scalar path
 };
 
 template <int SRC>
@@ -248,119 +249,151 @@ typedef uint4 KeyRows[4][32];
 __device__ __forceinline__ int s16lo(unsigned w) { return (int)(short)(w & 0xFFFF); }
 __device__ __forceinline__ int s16hi(unsigned w) { return (int)w >> 16; }
 
-__device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<true> &rg, KeyRows &keys, char *arena,
+// Element-wise pass of the block quantiser on packed rows, scalar form: any quantiser (Q > 16383 thresholds
+// wrap in int16), partial blocks, the -32768 corner of s2u_ (utils.h:95-99).  Rewrites the ring rows in place
+// with the folded quantised values, parks the rank candidates' keys (value << 4 | 15 - raster) and returns
+// the number of sure non-zeros; nc = number of candidates (tsuqBlock, bandcodec.cpp:166-186).
+template <int RR, class RingT>
+__device__ __forceinline__ int quant_rows_scalar(RingT &rg, KeyRows &keys, const QuantBand *qb, int o, int y0, int bw, int bh,
+                                                 int lane, int &nc)
+{
+	const bool full = bw == 4 && bh == 4;
+	const int T = full ? qb->T : qb->Te;
+	const unsigned T2 = (unsigned)(2 * T);
+	const int iQ = qb->iQ;
+	const unsigned uthr0 = full ? (unsigned)(qb->thr[0] & 0xFFFF) : 0u;  // partial blocks have no candidates
+	int cnt = 0;
+	nc = 0;
+#pragma unroll 1
+	for (int r = 0; r < 4; r++) {
+		uint2 &row = rg.v[o][(y0 + r) & (RR - 1)][lane];
+		const uint2 wv = row;
+		const int v[4] = {s16lo(wv.x), s16hi(wv.x), s16lo(wv.y), s16hi(wv.y)};
+		int out[4], key[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const bool live = j < bw && r < bh && (unsigned)(v[j] + T) > T2;
+			const int sgn = (int)((unsigned)v[j] >> 31);
+			const unsigned uf = (unsigned)(2 * abs(v[j]) + sgn) & 0xFFFFu;  // s2u_ (utils.h:95-99), C-typed
+			const bool cand = live && uf < uthr0;
+			const int qq = ((int)(uf >> 1) * iQ + (1 << 15)) >> 16;          // int arithmetic as in the reference (:172)
+			out[j] = !live ? 0 : cand ? (2 | sgn) : ((qq << 1) | sgn);
+			key[j] = cand ? (int)(uf << 4) | (15 - 4 * r - j) : 0;
+			cnt += (live && !cand) ? 1 : 0;
+			nc += cand ? 1 : 0;
+		}
+		row = make_uint2((unsigned)(out[0] & 0xFFFF) | ((unsigned)out[1] << 16), (unsigned)(out[2] & 0xFFFF) | ((unsigned)out[3] << 16));
+		keys[r][lane] = make_uint4((unsigned)key[0], (unsigned)key[1], (unsigned)key[2], (unsigned)key[3]);
+	}
+	return cnt;
+}
+
+// Rank stage on the parked 32-bit keys (tsuqBlock :188-199): which candidates survive.  Returns how many.
+template <int RR, class RingT>
+__device__ __forceinline__ int rank_rows_scalar(RingT &rg, KeyRows &keys, const QuantBand *qb, int o, int y0, int lane, int cnt, int ncm)
+{
+	int s[16];
+#pragma unroll
+	for (int r = 0; r < 4; r++) {
+		const uint4 kk = keys[r][lane];
+		s[4 * r] = (int)kk.x; s[4 * r + 1] = (int)kk.y; s[4 * r + 2] = (int)kk.z; s[4 * r + 3] = (int)kk.w;
+	}
+	int kstar = 0x7fffffff, m = 0;
+	if (ncm == 1) {  // at most one candidate per block: rank 0, survives iff f >= thr[cnt]
+		int s0 = 0;
+#pragma unroll
+		for (int k = 0; k < 16; k++) s0 = max(s0, s[k]);
+		bool pass;
+		if (qb->fast) pass = s0 >= qb->kthr[cnt];
+		else pass = s0 != 0 && !((int)(short)(s0 >> 4) < qb->thr[cnt & 15]);
+		if (pass && s0 != 0) { kstar = s0; m = 1; }
+	} else {
+		sort16_desc(s);
+		if (__builtin_expect(qb->fast, 1)) {
+			const int *kt = qb->kthr + cnt;
+#pragma unroll
+			for (int i = 0; i < 16; i++) {
+				if ((i & 3) == 0 && i >= ncm) break;  // warp-uniform
+				const bool pass = s[i] >= kt[i];
+				kstar = pass ? s[i] : kstar;
+				m = pass ? i + 1 : m;
+			}
+		} else {
+			// irregular thresholds (Q > 16383: int16 wrap in thr[]): rank every candidate against the
+			// parked keys with the reference's signed compare (:191); rolled, rare, small
+#pragma unroll 1
+			for (int i = 0; i < 16; i++) {
+				const int ki = ((const int *)&keys[i >> 2][lane])[i & 3];
+				if (ki == 0) continue;
+				int rank = 0;
+#pragma unroll 1
+				for (int j = 0; j < 16; j++) rank += ((const int *)&keys[j >> 2][lane])[j & 3] > ki;
+				if (!((int)(short)(ki >> 4) < qb->thr[(cnt + rank) & 15]) && rank + 1 > m) { m = rank + 1; kstar = ki; }
+			}
+		}
+	}
+	// drop the candidates ranked below the last survivor (:191-192)
+	const unsigned lim = (unsigned)(kstar - 1);
+#pragma unroll 1
+	for (int r = 0; r < 4; r++) {
+		const uint4 kk = keys[r][lane];
+		uint2 &row = rg.v[o][(y0 + r) & (RR - 1)][lane];
+		uint2 wv = row;
+		const unsigned m0 = (kk.x - 1u < lim) ? 0xFFFF0000u : 0xFFFFFFFFu, m1 = (kk.y - 1u < lim) ? 0x0000FFFFu : 0xFFFFFFFFu;
+		const unsigned m2 = (kk.z - 1u < lim) ? 0xFFFF0000u : 0xFFFFFFFFu, m3 = (kk.w - 1u < lim) ? 0x0000FFFFu : 0xFFFFFFFFu;
+		wv.x &= m0 & m1;
+		wv.y &= m2 & m3;
+		row = wv;
+	}
+	return m;
+}
+
+// RingT: anything with `uint2 v[3][RR][32]` (RR rows per band, a power of two); bands [o_begin, o_end).
+template <int RR, class RingT>
+__device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &rg, KeyRows &keys, char *arena,
                                                     unsigned char *flags, const QuantBand *qb3, int bx, int by, int lane,
-                                                    bool lane_out)
+                                                    bool lane_out, int o_begin = 0, int o_end = 3)
 {
 #pragma unroll 1
-	for (int o = 0; o < 3; o++) {
+	for (int o = o_begin; o < o_end; o++) {
 		const BandRef &b = P.band[o];
 		const int x0 = bx * 4, y0 = by * 4;
 		if (y0 >= b.dimy) continue;  // warp-uniform
 		const bool have = lane_out && x0 < b.dimx;
 		const int bw = have ? min(4, b.dimx - x0) : 0, bh = min(4, b.dimy - y0);
 		bool mark = false;
+		uint2 rows[4];
+#pragma unroll
+		for (int r = 0; r < 4; r++) rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
 		if (P.quant) {
 			const QuantBand *qb = qb3 + o;
 			const bool full = bw == 4 && bh == 4;
 			const int T = full ? qb->T : qb->Te;
-			const unsigned T2 = (unsigned)(2 * T);
 			int cnt = 0;
-			// pass 1: anything outside the dead zone in this warp's blocks?  (regular thresholds: packed min/max trees)
-			bool any_alive = have;
-			if (__builtin_expect(qb->fast && full, 1)) {
-				const uint2 r0 = rg.v[o][(y0 + 0) & (RING_ROWS - 1)][lane], r1 = rg.v[o][(y0 + 1) & (RING_ROWS - 1)][lane],
-				            r2 = rg.v[o][(y0 + 2) & (RING_ROWS - 1)][lane], r3 = rg.v[o][(y0 + 3) & (RING_ROWS - 1)][lane];
-				const unsigned mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(r0.x, r0.y, r1.x), __vimax3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
-				const unsigned mn = __vmins2(__vimin3_s16x2(__vimin3_s16x2(r0.x, r0.y, r1.x), __vimin3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
-				any_alive = max(s16lo(mx), s16hi(mx)) > T || min(s16lo(mn), s16hi(mn)) < -T;
-			}
+			// pass 1: anything outside the dead zone in this warp's blocks?  (packed min / max trees; rows and
+			// columns beyond the band hold finite garbage, which can only make the answer conservative)
+			const unsigned mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(rows[0].x, rows[0].y, rows[1].x), __vimax3_s16x2(rows[1].y, rows[2].x, rows[2].y), rows[3].x), rows[3].y);
+			const unsigned mn = __vmins2(__vimin3_s16x2(__vimin3_s16x2(rows[0].x, rows[0].y, rows[1].x), __vimin3_s16x2(rows[1].y, rows[2].x, rows[2].y), rows[3].x), rows[3].y);
+			const int vmax = max(s16lo(mx), s16hi(mx)), vmin = min(s16lo(mn), s16hi(mn));
+			const bool any_alive = have && (!qb->fast || vmax > T || vmin < -T);
 			if (__any_sync(FULL, any_alive)) {
-				// pass 2: fold, split into sure non-zeros (quantised now) and rank candidates (tsuqBlock :166-186)
-				const int iQ = qb->iQ;
-				const unsigned uthr0 = full ? (unsigned)(qb->thr[0] & 0xFFFF) : 0u;  // partial blocks have no candidates
-				int nc = 0;
-#pragma unroll 1
-				for (int r = 0; r < 4; r++) {
-					uint2 &row = rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane];
-					const uint2 wv = row;
-					const int v[4] = {s16lo(wv.x), s16hi(wv.x), s16lo(wv.y), s16hi(wv.y)};
-					int out[4], key[4];
+				int nc;
+				const bool pk = qb->pk && !__any_sync(FULL, vmin == -32768);  // warp-uniform
+				if (pk) {
+					uint2 keyr[4];
+					cnt = quant_rows_pk(qb, bw, bh, rows, keyr, nc);
+					const int ncm = __reduce_max_sync(FULL, nc);  // largest candidate count among this warp's blocks
+					if (ncm > 0) cnt += rank_rows_pk(qb, cnt, ncm, keyr, rows);
+				} else {
+					cnt = quant_rows_scalar<RR>(rg, keys, qb, o, y0, bw, bh, lane, nc);
+					const int ncm = __reduce_max_sync(FULL, nc);
+					if (ncm > 0) cnt += rank_rows_scalar<RR>(rg, keys, qb, o, y0, lane, cnt, ncm);
 #pragma unroll
-					for (int j = 0; j < 4; j++) {
-						const bool live = j < bw && r < bh && (unsigned)(v[j] + T) > T2;
-						const int sgn = (int)((unsigned)v[j] >> 31);
-						const unsigned uf = (unsigned)(2 * abs(v[j]) + sgn) & 0xFFFFu;  // s2u_ (utils.h:95-99), C-typed
-						const bool cand = live && uf < uthr0;
-						const int qq = ((int)(uf >> 1) * iQ + (1 << 15)) >> 16;          // int arithmetic as in the reference (:172)
-						out[j] = !live ? 0 : cand ? (2 | sgn) : ((qq << 1) | sgn);
-						key[j] = cand ? (int)(uf << 4) | (15 - 4 * r - j) : 0;
-						cnt += (live && !cand) ? 1 : 0;
-						nc += cand ? 1 : 0;
-					}
-					row = make_uint2((unsigned)(out[0] & 0xFFFF) | ((unsigned)out[1] << 16), (unsigned)(out[2] & 0xFFFF) | ((unsigned)out[3] << 16));
-					keys[r][lane] = make_uint4((unsigned)key[0], (unsigned)key[1], (unsigned)key[2], (unsigned)key[3]);
-				}
-				const int ncm = __reduce_max_sync(FULL, nc);  // largest candidate count among this warp's blocks
-				if (ncm > 0) {
-					int s[16];
-#pragma unroll
-					for (int r = 0; r < 4; r++) {
-						const uint4 kk = keys[r][lane];
-						s[4 * r] = (int)kk.x; s[4 * r + 1] = (int)kk.y; s[4 * r + 2] = (int)kk.z; s[4 * r + 3] = (int)kk.w;
-					}
-					int kstar = 0x7fffffff, m = 0;
-					if (ncm == 1) {  // at most one candidate per block: rank 0, survives iff f >= thr[cnt]
-						int s0 = 0;
-#pragma unroll
-						for (int k = 0; k < 16; k++) s0 = max(s0, s[k]);
-						bool pass;
-						if (qb->fast) pass = s0 >= qb->kthr[cnt];
-						else pass = s0 != 0 && !((int)(short)(s0 >> 4) < qb->thr[cnt & 15]);
-						if (pass && s0 != 0) { kstar = s0; m = 1; }
-					} else {
-						sort16_desc(s);
-						if (__builtin_expect(qb->fast, 1)) {
-							const int *kt = qb->kthr + cnt;
-#pragma unroll
-							for (int i = 0; i < 16; i++) {
-								if ((i & 3) == 0 && i >= ncm) break;  // warp-uniform
-								const bool pass = s[i] >= kt[i];
-								kstar = pass ? s[i] : kstar;
-								m = pass ? i + 1 : m;
-							}
-						} else {
-							// irregular thresholds (Q > 16383: int16 wrap in thr[]): rank every candidate against the
-							// parked keys with the reference's signed compare (:191); rolled, rare, small
-#pragma unroll 1
-							for (int i = 0; i < 16; i++) {
-								const int ki = ((const int *)&keys[i >> 2][lane])[i & 3];
-								if (ki == 0) continue;
-								int rank = 0;
-#pragma unroll 1
-								for (int j = 0; j < 16; j++) rank += ((const int *)&keys[j >> 2][lane])[j & 3] > ki;
-								if (!((int)(short)(ki >> 4) < qb->thr[(cnt + rank) & 15]) && rank + 1 > m) { m = rank + 1; kstar = ki; }
-							}
-						}
-					}
-					// drop the candidates ranked below the last survivor (:191-192)
-					const unsigned lim = (unsigned)(kstar - 1);
-#pragma unroll 1
-					for (int r = 0; r < 4; r++) {
-						const uint4 kk = keys[r][lane];
-						uint2 &row = rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane];
-						uint2 wv = row;
-						const unsigned m0 = (kk.x - 1u < lim) ? 0xFFFF0000u : 0xFFFFFFFFu, m1 = (kk.y - 1u < lim) ? 0x0000FFFFu : 0xFFFFFFFFu;
-						const unsigned m2 = (kk.z - 1u < lim) ? 0xFFFF0000u : 0xFFFFFFFFu, m3 = (kk.w - 1u < lim) ? 0x0000FFFFu : 0xFFFFFFFFu;
-						wv.x &= m0 & m1;
-						wv.y &= m2 & m3;
-						row = wv;
-					}
-					cnt += m;
+					for (int r = 0; r < 4; r++) rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
 				}
 			} else {
 #pragma unroll
-				for (int r = 0; r < 4; r++) rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane] = make_uint2(0u, 0u);
+				for (int r = 0; r < 4; r++) rows[r] = make_uint2(0u, 0u);
 			}
 			int nz = cnt;
 			if (P.has_child && bw == 4 && bh == 4) {  // buildTree :267-270: add the four child blocks
@@ -372,18 +405,22 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, Ring<tru
 			mark = nz == 0;  // INSIGNIF_BLOCK in the block's first sample, bandcodec.cpp:113,272
 		}
 		if (!have) continue;
-		char *base = arena + b.off;
-#pragma unroll 1
-		for (int r = 0; r < bh; r++) {
-			uint2 wv = rg.v[o][(y0 + r) & (RING_ROWS - 1)][lane];
-			if (r == 0 && mark) wv.x = (wv.x & 0xFFFF0000u) | 0x8000u;
-			char *rowp = base + (long long)(y0 + r) * b.stride * 2 + 2 * (long long)x0;
-			if (bw == 4) *(uint2 *)rowp = wv;
-			else {
-				if (bw > 0) ((short *)rowp)[0] = (short)(wv.x & 0xFFFF);
-				if (bw > 1) ((short *)rowp)[1] = (short)(wv.x >> 16);
-				if (bw > 2) ((short *)rowp)[2] = (short)(wv.y & 0xFFFF);
-			}
+		if (mark) rows[0].x = (rows[0].x & 0xFFFF0000u) | 0x8000u;
+		char *rowp = arena + b.off + ((long long)y0 * b.stride + x0) * 2;
+		const long long pitch = (long long)b.stride * 2;
+		if (bw == 4) {
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+				if (r < bh) *(uint2 *)(rowp + r * pitch) = rows[r];
+		} else {
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+				if (r < bh) {
+					short *q = (short *)(rowp + r * pitch);
+					if (bw > 0) q[0] = (short)(rows[r].x & 0xFFFF);
+					if (bw > 1) q[1] = (short)(rows[r].x >> 16);
+					if (bw > 2) q[2] = (short)(rows[r].y & 0xFFFF);
+				}
 		}
 	}
 }
@@ -506,7 +543,7 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<S
 		if ((jv & 3) == 3) {  // block row jv>>2 of D, H and V is complete (D/H rows sit one slot ahead in the ring)
 			const int by = jv >> 2;
 			if (by >= (y0 >> 3)) {
-				if constexpr (SH) flush_blocks_packed(P, rg, keys, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
+				if constexpr (SH) flush_blocks_packed<RING_ROWS>(P, rg, keys, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
 				else flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
 			}
 		}

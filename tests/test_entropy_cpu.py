@@ -209,3 +209,20 @@ def test_random_geometries_match_reference():
             o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
         assert np.array_equal(back, arenas), (w, h, ch, q, levels, lc, trans, kind)
         done += 1
+
+
+@pytest.mark.parametrize("fill", [0xFF, 0x55, 0xAA, 0x00, 0x5A])
+@pytest.mark.parametrize("ch", [1, 3])
+def test_pathological_payloads_are_rejected_not_crashing(fill, ch):
+    """ADVICE r1: a payload without two consecutive zero bits used to run MuxReader::taboo() past its 32-entry
+    tables (and corrupt streams could push the Golomb parameter past 31).  Such payloads must come back as an
+    error (RIC_E_ARG) or decode to *something* -- never touch memory outside the tables."""
+    w, h = 64, 48
+    o = oraclebind.Oracle(w, h, 5)
+    for size in (1, 7, 64, 4096):
+        payload = np.full(size, fill, dtype=np.uint8)
+        back = np.zeros(o.arena_bytes * ch, dtype=np.uint8)
+        try:
+            capi.entropy_decode(w, h, ch, payload, back)
+        except capi.RicError as e:
+            assert e.code == -1, e  # RIC_E_ARG
