@@ -27,6 +27,13 @@ using namespace ric;
 
 static thread_local char g_err[512] = "";
 
+static int getenv(const char *name, int dflt)
+{
+	const char *v = ::getenv(name);
+	return v ? atoi(v) : dflt;
+}
+
+
 static int set_err(int code, const char *fmt, const char *a = "", const char *b = "")
 {
 	snprintf(g_err, sizeof g_err, fmt, a, b);
@@ -78,7 +85,7 @@ struct ric_ctx {
 	cudaEvent_t ev[2][RIC_MAX_LEVELS + 1];  // [direction][launch boundary]
 	int ev_n[2];
 	int target_warps;
-	int use_fwd0;                        // packed level-0 forward kernel (RIC_FWD0=0 switches back to the scalar one)
+	int use_fwd0;                        // packed level-0 forward kernel, experimental (RIC_FWD0=1)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -193,12 +200,6 @@ __global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-
-static int getenv(const char *name, int dflt)
-{
-	const char *v = ::getenv(name);
-	return v ? atoi(v) : dflt;
-}
 
 static void fill_qb(QuantBand &q, int Quant, int lambda, float weight, int is_int)
 {
@@ -333,8 +334,9 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	c->sm_count = prop.multiProcessorCount;
 	const char *tw = getenv("RIC_TARGET_WARPS");
 	c->target_warps = tw ? atoi(tw) : 0;  // override of the concurrent-job count used by choose_seg_rows
-	const char *f0 = getenv("RIC_FWD0");
-	c->use_fwd0 = f0 ? atoi(f0) : 1;
+	// ric_fwd0.cuh: measured 6 % slower than the scalar kernel with the packed quantiser (12 warps per SM against
+	// 16: profiles/README.md), so it is opt-in
+	c->use_fwd0 = getenv("RIC_FWD0", 0);
 #define CKD(call)                                                                    \
 	do {                                                                             \
 		cudaError_t e_ = (call);                                                     \

@@ -348,8 +348,30 @@ __device__ __forceinline__ int rank_rows_scalar(RingT &rg, KeyRows &keys, const 
 	return m;
 }
 
-// RingT: anything with `uint2 v[3][RR][32]` (RR rows per band, a power of two); bands [o_begin, o_end).
+// lane-private row / key staging of one block for the packed quantiser (ric_quant_pk.cuh): in shared memory ...
 template <int RR, class RingT>
+struct BlockIO {
+	static constexpr int UNROLL = 1;
+	RingT &rg;
+	KeyRows &keys;
+	int o, y0, lane;
+	__device__ __forceinline__ uint2 get(int r) const { return rg.v[o][(y0 + r) & (RR - 1)][lane]; }
+	__device__ __forceinline__ void put(int r, uint2 v) { rg.v[o][(y0 + r) & (RR - 1)][lane] = v; }
+	__device__ __forceinline__ uint2 get_key(int r) const { return *(const uint2 *)&keys[r][lane]; }
+	__device__ __forceinline__ void put_key(int r, uint2 v) { *(uint2 *)&keys[r][lane] = v; }
+};
+// ... or in registers (every index is a compile-time constant once the loops are flat)
+struct RegIO {
+	static constexpr int UNROLL = 2;
+	uint2 rows[4], keyr[4];
+	__device__ __forceinline__ uint2 get(int r) const { return rows[r]; }
+	__device__ __forceinline__ void put(int r, uint2 v) { rows[r] = v; }
+	__device__ __forceinline__ uint2 get_key(int r) const { return keyr[r]; }
+	__device__ __forceinline__ void put_key(int r, uint2 v) { keyr[r] = v; }
+};
+
+// RingT: anything with `uint2 v[3][RR][32]` (RR rows per band, a power of two); bands [o_begin, o_end).
+template <int RR, bool FLAT = true, class RingT>
 __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &rg, KeyRows &keys, char *arena,
                                                     unsigned char *flags, const QuantBand *qb3, int bx, int by, int lane,
                                                     bool lane_out, int o_begin = 0, int o_end = 3)
@@ -362,9 +384,9 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 		const bool have = lane_out && x0 < b.dimx;
 		const int bw = have ? min(4, b.dimx - x0) : 0, bh = min(4, b.dimy - y0);
 		bool mark = false;
-		uint2 rows[4];
+		RegIO io;  // FLAT: the block stays in registers from here to the band stores
 #pragma unroll
-		for (int r = 0; r < 4; r++) rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
+		for (int r = 0; r < 4; r++) io.rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
 		if (P.quant) {
 			const QuantBand *qb = qb3 + o;
 			const bool full = bw == 4 && bh == 4;
@@ -372,28 +394,40 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 			int cnt = 0;
 			// pass 1: anything outside the dead zone in this warp's blocks?  (packed min / max trees; rows and
 			// columns beyond the band hold finite garbage, which can only make the answer conservative)
-			const unsigned mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(rows[0].x, rows[0].y, rows[1].x), __vimax3_s16x2(rows[1].y, rows[2].x, rows[2].y), rows[3].x), rows[3].y);
-			const unsigned mn = __vmins2(__vimin3_s16x2(__vimin3_s16x2(rows[0].x, rows[0].y, rows[1].x), __vimin3_s16x2(rows[1].y, rows[2].x, rows[2].y), rows[3].x), rows[3].y);
+			const uint2 r0 = io.rows[0], r1 = io.rows[1], r2 = io.rows[2], r3 = io.rows[3];
+			const unsigned mx = __vmaxs2(__vimax3_s16x2(__vimax3_s16x2(r0.x, r0.y, r1.x), __vimax3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
+			const unsigned mn = __vmins2(__vimin3_s16x2(__vimin3_s16x2(r0.x, r0.y, r1.x), __vimin3_s16x2(r1.y, r2.x, r2.y), r3.x), r3.y);
 			const int vmax = max(s16lo(mx), s16hi(mx)), vmin = min(s16lo(mn), s16hi(mn));
 			const bool any_alive = have && (!qb->fast || vmax > T || vmin < -T);
+			bool in_regs = FLAT;  // where the quantised block is: io.rows or the ring
 			if (__any_sync(FULL, any_alive)) {
 				int nc;
-				const bool pk = qb->pk && !__any_sync(FULL, vmin == -32768);  // warp-uniform
-				if (pk) {
-					uint2 keyr[4];
-					cnt = quant_rows_pk(qb, bw, bh, rows, keyr, nc);
-					const int ncm = __reduce_max_sync(FULL, nc);  // largest candidate count among this warp's blocks
-					if (ncm > 0) cnt += rank_rows_pk(qb, cnt, ncm, keyr, rows);
+				// the packed form does not cover the -32768 corner of s2u_ (utils.h:95-99): warp-uniform choice
+				if (qb->pk && !__any_sync(FULL, vmin == -32768)) {
+					if constexpr (FLAT) {
+						cnt = quant_rows_pk(qb, bw, bh, io, nc);
+						const int ncm = __reduce_max_sync(FULL, nc);  // largest candidate count among this warp's blocks
+						if (ncm > 0) cnt += rank_rows_pk(qb, cnt, ncm, io);
+					} else {
+						BlockIO<RR, RingT> sio{rg, keys, o, y0, lane};
+						cnt = quant_rows_pk(qb, bw, bh, sio, nc);
+						const int ncm = __reduce_max_sync(FULL, nc);
+						if (ncm > 0) cnt += rank_rows_pk(qb, cnt, ncm, sio);
+					}
 				} else {
 					cnt = quant_rows_scalar<RR>(rg, keys, qb, o, y0, bw, bh, lane, nc);
 					const int ncm = __reduce_max_sync(FULL, nc);
 					if (ncm > 0) cnt += rank_rows_scalar<RR>(rg, keys, qb, o, y0, lane, cnt, ncm);
-#pragma unroll
-					for (int r = 0; r < 4; r++) rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
+					in_regs = false;
 				}
 			} else {
 #pragma unroll
-				for (int r = 0; r < 4; r++) rows[r] = make_uint2(0u, 0u);
+				for (int r = 0; r < 4; r++) io.rows[r] = make_uint2(0u, 0u);
+				in_regs = true;
+			}
+			if (!in_regs) {
+#pragma unroll
+				for (int r = 0; r < 4; r++) io.rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
 			}
 			int nz = cnt;
 			if (P.has_child && bw == 4 && bh == 4) {  // buildTree :267-270: add the four child blocks
@@ -405,22 +439,20 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 			mark = nz == 0;  // INSIGNIF_BLOCK in the block's first sample, bandcodec.cpp:113,272
 		}
 		if (!have) continue;
-		if (mark) rows[0].x = (rows[0].x & 0xFFFF0000u) | 0x8000u;
+		if (mark) io.rows[0].x = (io.rows[0].x & 0xFFFF0000u) | 0x8000u;
 		char *rowp = arena + b.off + ((long long)y0 * b.stride + x0) * 2;
 		const long long pitch = (long long)b.stride * 2;
-		if (bw == 4) {
 #pragma unroll
-			for (int r = 0; r < 4; r++)
-				if (r < bh) *(uint2 *)(rowp + r * pitch) = rows[r];
-		} else {
-#pragma unroll
-			for (int r = 0; r < 4; r++)
-				if (r < bh) {
-					short *q = (short *)(rowp + r * pitch);
-					if (bw > 0) q[0] = (short)(rows[r].x & 0xFFFF);
-					if (bw > 1) q[1] = (short)(rows[r].x >> 16);
-					if (bw > 2) q[2] = (short)(rows[r].y & 0xFFFF);
-				}
+		for (int r = 0; r < 4; r++) {
+			if (r >= bh) break;  // warp-uniform
+			const uint2 wv = io.rows[r];
+			if (bw == 4) *(uint2 *)(rowp + r * pitch) = wv;
+			else {
+				short *q = (short *)(rowp + r * pitch);
+				if (bw > 0) q[0] = (short)(wv.x & 0xFFFF);
+				if (bw > 1) q[1] = (short)(wv.x >> 16);
+				if (bw > 2) q[2] = (short)(wv.y & 0xFFFF);
+			}
 		}
 	}
 }

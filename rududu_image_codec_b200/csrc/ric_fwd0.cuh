@@ -181,9 +181,21 @@ __device__ __noinline__ bool f0_v_slow(uint4 *scr, uint4 *st, int t, int h)
 	return ok;
 }
 
+// Strips that hold column 0 or column w-1 (2 of 16 at 4K): the row pass with the reference's edge formulas, and
+// the columns outside the image zeroed (they hold garbage, and the packed column pass must stay in range).
+// Out of line: the hot loop must stay small (instruction cache), and this is the rarer case.
+__device__ __noinline__ void f0_row_pass_edge(unsigned (&X)[8], int cb, int w, int nvalid)
+{
+	using namespace sw;
+	const EdgeX ex = make_edge_x(cb, w, true);
+	f0_row_pass<true>(X, ex);
+#pragma unroll
+	for (int k = 0; k < 8; k++) X[k] = k < nvalid ? X[k] : ((k & 1) ? KH::O4 : KH::E3);
+}
+
 // One job = one (image, row segment, strip), all NP planes.
-template <int NP, bool EDGE>
-__device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, int sx, F0Smem<NP> &sm,
+template <int NP>
+__device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, int sx, bool EDGE, F0Smem<NP> &sm,
                                          const QuantBand (*s_qb)[3], int lane)
 {
 	using namespace sw;
@@ -192,7 +204,6 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 	const int cb = x0 - LANE_W + lane * LANE_W;
 	const bool col_ok = cb >= 0 && cb < w;
 	const bool lane_out = lane >= 1 && lane <= 30;
-	const EdgeX ex = make_edge_x(cb, w, EDGE);
 	const int nvalid = cb < 0 ? 0 : min(8, max(0, w - cb));  // real columns of this lane (EDGE strips only)
 	const int y0 = sy * P.seg_rows;
 	const int y1 = min(h, y0 + P.seg_rows);
@@ -257,10 +268,17 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 				const uint4 a = sm.stage[p][0][lane], b = sm.stage[p][1][lane];
 				X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
 			}
-			f0_row_pass<EDGE>(X, ex);
-			if (EDGE) {  // columns outside the image hold garbage: zero them, the packed column pass must stay in range
+			if (EDGE) {  // warp-uniform; a copy goes through the call so that X itself stays in registers
+				unsigned Y[8];
 #pragma unroll
-				for (int k = 0; k < 8; k++) X[k] = k < nvalid ? X[k] : ((k & 1) ? KH::O4 : KH::E3);
+				for (int k = 0; k < 8; k++) Y[k] = X[k];
+				f0_row_pass_edge(Y, cb, w, nvalid);
+#pragma unroll
+				for (int k = 0; k < 8; k++) X[k] = Y[k];
+			} else {
+				EdgeX none;
+				none.on = false;
+				f0_row_pass<false>(X, none);
 			}
 			// transpose: two columns of one row per register (even columns first: D / V, then odd: H / LL)
 			unsigned NE[4], NO[4];
@@ -323,7 +341,7 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 				for (int p = 0; p < NP; p++) {
 					char *arena = P.arena + img * P.arena_img_stride + p * P.arena_plane_stride;
 					unsigned char *flags = P.flags + img * P.flags_img_stride + p * P.flags_plane_stride;
-					flush_blocks_packed<F0_RR>(P, sm.ring[p], sm.keys, arena, flags, &s_qb[P.plane_class[p]][0], bx, by, lane, lane_out,
+					flush_blocks_packed<F0_RR, false>(P, sm.ring[p], sm.keys, arena, flags, &s_qb[P.plane_class[p]][0], bx, by, lane, lane_out,
 					                           dh ? 0 : 2, dh ? 2 : 3);
 				}
 			}
@@ -351,8 +369,7 @@ __global__ void __launch_bounds__(F0_WARPS * 32, NP == 3 ? 3 : 4) fwd0_kernel(co
 		const int sy = (int)(job % (unsigned)P.nsegs);
 		const int img = (int)(job / (unsigned)P.nsegs);
 		const int x0 = sx * STRIP_W;
-		if ((x0 == 0) || (P.w <= x0 + STRIP_W + LANE_W)) fwd0_job<NP, true>(P, img, sy, sx, sm, s_qb, lane);
-		else fwd0_job<NP, false>(P, img, sy, sx, sm, s_qb, lane);
+		fwd0_job<NP>(P, img, sy, sx, (x0 == 0) || (P.w <= x0 + STRIP_W + LANE_W), sm, s_qb, lane);
 	}
 }
 

@@ -69,7 +69,11 @@ RIC_HD void sort16_desc(int (&s)[16])
 // as signed half-words candidates are negative and everything else is zero, so "ranked below the last survivor"
 // is one packed subtract and a sign spread.  Needs (host-checked, fill_qb): 4 <= Q, thr[0] - 2T < 2047,
 // sure samples quantise to >= 1; and no -32768 in the block (the caller checks: s2u_ wraps there).
-RIC_HD int quant_rows_pk(const QuantBand *qb, int bw, int bh, uint2 (&rows)[4], uint2 (&keyr)[4], int &nc)
+// IO: get(r) / put(r, row) the block's row r (4 packed samples), get_key(r) / put_key(r, keys): lane-private staging.
+// IO::UNROLL == 1: rows two at a time in a rolled loop over shared-memory staging (kernels whose hot loop is at the
+// limit of the instruction cache: ric_fwd0.cuh); IO::UNROLL == 2: flat code on registers (ric_fwd.cuh).
+template <class IO>
+RIC_HD int quant_rows_pk(const QuantBand *qb, int bw, int bh, IO &io, int &nc)  // IO::UNROLL: 1 (rolled) or 2 (flat)
 {
 	const bool full = bw == 4 && bh == 4;
 	const int T = full ? qb->T : qb->Te;
@@ -81,46 +85,53 @@ RIC_HD int quant_rows_pk(const QuantBand *qb, int bw, int bh, uint2 (&rows)[4], 
 	const unsigned NT = (unsigned)((-T) & 0xFFFF) * 0x10001u;
 	const unsigned iQ = (unsigned)qb->iQ, iQ2 = 2u * iQ;
 	unsigned accL = 0, accS = 0;
+#pragma unroll IO::UNROLL
+	for (int r0 = 0; r0 < 4; r0 += 2) {
 #pragma unroll
-	for (int r = 0; r < 4; r++) {
-		if (r >= bh) { rows[r] = make_uint2(0u, 0u); keyr[r] = make_uint2(0u, 0u); continue; }  // warp-uniform
-		unsigned out[2], key[2];
+		for (int rr = 0; rr < 2; rr++) {
+			const int r = r0 + rr;
+			if (r >= bh) { io.put(r, make_uint2(0u, 0u)); io.put_key(r, make_uint2(0u, 0u)); continue; }  // warp-uniform
+			const uint2 row = io.get(r);
+			unsigned out[2], key[2];
 #pragma unroll
-		for (int g = 0; g < 2; g++) {
-			const unsigned w = g ? rows[r].y : rows[r].x;
-			const unsigned a = sw::viaddmax2(~w, 0x00010001u, w);                  // |w|
-			const unsigned LM = sw::smear(sw::vadd2(a, cl[g]));             // outside the dead zone
-			const unsigned SM = sw::smear(sw::vadd2(a, cs[g]));             // f >= thr[0]: quantised for sure
-			const unsigned sb = (w >> 15) & LM & 0x00010001u;                          // sign bit of the live samples
-			const unsigned al = a & LM;
-			const unsigned p0 = (al & 0xFFFFu) * iQ + 32768u;                          // (|c| * iQ + 32768) >> 16, :172
-			const unsigned p1 = (al >> 16) * iQ2 + 65536u;                             // the same, already doubled
-			const unsigned t = (p1 & 0xFFFE0000u) | ((p0 >> 15) & 0x0000FFFFu);
-			const unsigned CM = LM & ~SM;                                              // rank candidates
-			out[g] = (t & 0xFFFEFFFEu) | sb | (CM & 0x00020002u);
-			accL = sw::vadd2(accL, LM);
-			accS = sw::vadd2(accS, SM);
-			const unsigned m = sw::vadd2(a, NT);                                        // |c| - T
-			const unsigned f2 = sw::vadd2(sw::vadd2(m, m), sb) & CM;                      // f - 2T (candidates only)
-			const unsigned pos = 4u * r + 2u * g;
-			key[g] = ((f2 * 16u) | ((0x8000u | (14u - pos)) << 16) | (0x8000u | (15u - pos))) & CM;
+			for (int g = 0; g < 2; g++) {
+				const unsigned w = g ? row.y : row.x;
+				const unsigned a = sw::viaddmax2(~w, 0x00010001u, w);                  // |w|
+				const unsigned LM = sw::smear(sw::vadd2(a, cl[g]));                       // outside the dead zone
+				const unsigned SM = sw::smear(sw::vadd2(a, cs[g]));                       // f >= thr[0]: quantised for sure
+				const unsigned sb = (w >> 15) & LM & 0x00010001u;                          // sign bit of the live samples
+				const unsigned al = a & LM;
+				const unsigned p0 = (al & 0xFFFFu) * iQ + 32768u;                          // (|c| * iQ + 32768) >> 16, :172
+				const unsigned p1 = (al >> 16) * iQ2 + 65536u;                             // the same, already doubled
+				const unsigned t = (p1 & 0xFFFE0000u) | ((p0 >> 15) & 0x0000FFFFu);
+				const unsigned CM = LM & ~SM;                                              // rank candidates
+				out[g] = (t & 0xFFFEFFFEu) | sb | (CM & 0x00020002u);
+				accL = sw::vadd2(accL, LM);
+				accS = sw::vadd2(accS, SM);
+				const unsigned m = sw::vadd2(a, NT);                                      // |c| - T
+				const unsigned f2 = sw::vadd2(sw::vadd2(m, m), sb) & CM;                  // f - 2T (candidates only)
+				const unsigned pos = 4u * (unsigned)r + 2u * (unsigned)g;                  // tag | 15 - raster position, per half
+				key[g] = ((f2 * 16u) | (0x800E800Fu - pos * 0x00010001u)) & CM;
+			}
+			io.put(r, make_uint2(out[0], out[1]));
+			io.put_key(r, make_uint2(key[0], key[1]));
 		}
-		rows[r] = make_uint2(out[0], out[1]);
-		keyr[r] = make_uint2(key[0], key[1]);
 	}
 	const int nl = -((int)(short)(accL & 0xFFFF) + ((int)accL >> 16)), ns = -((int)(short)(accS & 0xFFFF) + ((int)accS >> 16));
 	nc = nl - ns;
 	return ns;
 }
 
-// Rank stage on the 16-bit keys: clears the halves of `rows` that belong to dropped candidates, returns the survivors.
-RIC_HD int rank_rows_pk(const QuantBand *qb, int cnt, int ncm, const uint2 (&keyr)[4], uint2 (&rows)[4])
+// Rank stage on the 16-bit keys: clears the halves of the rows that belong to dropped candidates, returns the survivors.
+template <class IO>
+RIC_HD int rank_rows_pk(const QuantBand *qb, int cnt, int ncm, IO &io)
 {
 	int s[16];
 #pragma unroll
 	for (int r = 0; r < 4; r++) {
-		s[4 * r] = (int)(keyr[r].x & 0xFFFFu); s[4 * r + 1] = (int)(keyr[r].x >> 16);
-		s[4 * r + 2] = (int)(keyr[r].y & 0xFFFFu); s[4 * r + 3] = (int)(keyr[r].y >> 16);
+		const uint2 k = io.get_key(r);
+		s[4 * r] = (int)(k.x & 0xFFFFu); s[4 * r + 1] = (int)(k.x >> 16);
+		s[4 * r + 2] = (int)(k.y & 0xFFFFu); s[4 * r + 3] = (int)(k.y >> 16);
 	}
 	int kstar = 0, m = 0;  // kstar: key of the last survivor (0: nobody survives)
 	if (ncm == 1) {
@@ -141,10 +152,13 @@ RIC_HD int rank_rows_pk(const QuantBand *qb, int cnt, int ncm, const uint2 (&key
 	}
 	// as signed half-words: candidates' keys are negative, everything else 0 -> (key - kstar) < 0 <=> dropped candidate
 	const unsigned nk = (unsigned)((-kstar) & 0xFFFF) * 0x10001u;
-#pragma unroll
+#pragma unroll (IO::UNROLL == 2 ? 4 : 1)
 	for (int r = 0; r < 4; r++) {
-		rows[r].x &= ~sw::smear(sw::vadd2(keyr[r].x, nk));
-		rows[r].y &= ~sw::smear(sw::vadd2(keyr[r].y, nk));
+		const uint2 k = io.get_key(r);
+		uint2 row = io.get(r);
+		row.x &= ~sw::smear(sw::vadd2(k.x, nk));
+		row.y &= ~sw::smear(sw::vadd2(k.y, nk));
+		io.put(r, row);
 	}
 	return m;
 }

@@ -36,14 +36,25 @@ static void fill_qb(QuantBand &q, int Quant, int lambda, float weight)
 	q.h0 = std::max(hq.thr[0] >> 1, hq.T + 1);
 }
 
-int main()
+template <int U>
+struct TestIOT {
+	static constexpr int UNROLL = U;
+	uint2 rows[4], keys[4];
+	uint2 get(int r) const { return rows[r]; }
+	void put(int r, uint2 v) { rows[r] = v; }
+	uint2 get_key(int r) const { return keys[r]; }
+	void put_key(int r, uint2 v) { keys[r] = v; }
+};
+
+template <int U>
+static void run()
 {
 	int tested = 0, skipped = 0;
 	// one-level geometry: every band is a finest band (no children), 9/7 weights D 1/s, H = V = 1
 	for (int iter = 0; iter < 400; iter++) {
 		const int w = 32 + (int)(rnd() % 40), h = 32 + (int)(rnd() % 40);
 		rico_geom g;
-		if (rico_geom_init(&g, w, h, 1, 0, 32, RICO_CDF97)) { printf("geom_init failed\n"); return 1; }
+		if (rico_geom_init(&g, w, h, 1, 0, 32, RICO_CDF97)) { printf("geom_init failed\n"); exit(1); }
 		static const int qs[] = {32, 42, 96, 126, 288, 380, 672, 1024, 2048, 2705, 9, 4, 5, 1500};
 		const int Quant = qs[iter % 14];
 		const int lambda = (iter % 5 == 4) ? 0 : (iter % 7 == 6) ? Quant : (int)(Quant / 2.4);
@@ -74,7 +85,9 @@ int main()
 			for (int by = 0; by * 4 < b.dimy; by++)
 				for (int bx = 0; bx * 4 < b.dimx; bx++) {
 					const int bw = std::min(4, b.dimx - 4 * bx), bh = std::min(4, b.dimy - 4 * by);
-					uint2 rows[4], keyr[4];
+					TestIOT<U> io;
+					uint2 (&rows)[4] = io.rows;
+					for (int r = 0; r < 4; r++) io.keys[r] = make_uint2(0xDEADBEEFu, 0x12345678u);  // stale staging
 					bool corner = false;
 					for (int r = 0; r < 4; r++) {
 						unsigned short v[4];
@@ -88,10 +101,10 @@ int main()
 					}
 					if (corner) { skipped++; continue; }  // flush_blocks_packed sends such warps to the scalar path
 					int nc;
-					int cnt = quant_rows_pk(&qb, bw, bh, rows, keyr, nc);
+					int cnt = quant_rows_pk(&qb, bw, bh, io, nc);
 					// the kernel passes the warp's largest candidate count: any value >= nc must give the same result
 					const int ncm = nc == 0 ? 0 : std::min(16, nc + (int)(rnd() % 3) * (int)(rnd() % 8));
-					if (ncm > 0) cnt += rank_rows_pk(&qb, cnt, ncm, keyr, rows);
+					if (ncm > 0) cnt += rank_rows_pk(&qb, cnt, ncm, io);
 					if (cnt == 0) rows[0].x = (rows[0].x & 0xFFFF0000u) | 0x8000u;  // INSIGNIF_BLOCK (single level: no children)
 					for (int r = 0; r < bh; r++)
 						for (int k = 0; k < bw; k++) {
@@ -105,8 +118,14 @@ int main()
 				}
 		}
 	}
-	printf("blocks tested %d, skipped (not pk / -32768 corner) %d\n", tested, skipped);
+	printf("unroll %d: blocks tested %d, skipped (not pk / -32768 corner) %d\n", U, tested, skipped);
 	CHECK(tested > 50000, "too few blocks tested");
+}
+
+int main()
+{
+	run<1>();
+	run<2>();
 	if (fails) { printf("quant_pk_test: %d FAILURES\n", fails); return 1; }
 	printf("quant_pk_test: ok\n");
 	return 0;
