@@ -36,10 +36,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--q", type=int, default=Q_)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--files-batch", type=int, default=1024,
-                    help="images in the device-entropy .ric file measurement (1080p RGB; 0 = skip)")
+                    help="images per GPU in the device-entropy .ric file measurement (1080p RGB; 0 = skip)")
+    ap.add_argument("--configs3-images", type=int, default=4096,
+                    help="global batch of the BASELINE configs[3] figures (1080p RGB, strong-scaled over the ranks; 0 = skip)")
     ap.add_argument("--workload", default="4k", choices=["4k", "1080p"],
                     help="4k: 3840x2160 RGB (BASELINE configs[1] shape, the judged line); 1080p: 1920x1080 RGB (configs[3])")
     args = ap.parse_args()
@@ -49,6 +51,17 @@ def parse():
         if args.batch == 32:
             args.batch = 128  # same bytes per step as 32 x 4K
     return args
+
+
+def workload_config(args):
+    """`config` of the JSON line: a function of the arguments only, so that both arms print the same object."""
+    px = args.batch * W_ * H_ * CH_
+    return {"workload": "%dx%d RGB (BASELINE configs[%d] shape), 5-level cdf97, q=%d, batch %d images per GPU, "
+                        "encode stage + decode stage per step" % (W_, H_, 1 if W_ == 3840 else 3, args.q, args.batch),
+            "batch_per_gpu": args.batch, "distinct_images_per_gpu": args.batch,
+            "l2": "inputs larger than L2 (%.0f MB of pixels and %.0f MB of band arenas read+written per GPU per step)"
+                  % (2 * px / 1e6, 4 * px / 1e6),
+            "sharding": "independent images per rank, no collective"}
 
 
 def load_peaks():
@@ -144,8 +157,7 @@ def run_reference(args):
         "unit": "Mpixel/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int16", "data": "synthetic",
-        "config": {"workload": "%dx%d RGB, 5-level cdf97, q=%d, encode+decode stage" % (W_, H_, args.q),
-                   "images_per_step": n_images, "host_threads": threads},
+        "config": workload_config(args), "sample_images_per_step": n_images, "host_threads": threads,
         "encode_mpix_s": n_images * args.steps * W_ * H_ / te / 1e6,
         "decode_mpix_s": n_images * args.steps * W_ * H_ / td / 1e6,
         "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": threads, "kind": "reference", "sample": sample},
@@ -214,7 +226,8 @@ def single_image_latency(capi, synth_image, dev, w, h, ch, levels, q, iters=10):
     return {"encode_ms": te, "decode_ms": td, "encode_mpix_s": px / te / 1e3, "decode_mpix_s": px / td / 1e3,
             "encode_frac": ALG_BYTES_PER_SAMPLE * px * ch / (te * 1e-3) / 1e9 / load_peaks()[0],
             "decode_frac": ALG_BYTES_PER_SAMPLE * px * ch / (td * 1e-3) / 1e9 / load_peaks()[0],
-            "l2": "flushed before every timed call", "iters": iters}
+            "l2": "flushed before every timed call", "iters": iters,
+            "decode_input": "the folded encode output (same work per sample as signed coefficients)"}
 
 
 def ric_file_throughput(L, ctx, h_src, h_dst, n, q, with_reference):
@@ -253,51 +266,209 @@ def ric_file_throughput(L, ctx, h_src, h_dst, n, q, with_reference):
     return out
 
 
-def ric_file_throughput_device(capi, L, dev_index, n, q):
-    """BASELINE configs[3] shape (1080p RGB, thousands of images; here n of them): images -> .ric files -> images
-    with the entropy stage on the device too (ric_compress_u8_gpu / ric_decompress_u8_gpu).  Pinned host buffers;
-    H2D of the pixels, all kernels, D2H of the finished files (and the reverse) inside the timed region."""
+def _check(L, rc):
+    if rc:
+        raise RuntimeError(L.ric_last_error().decode())
+
+
+def ric_file_throughput_device(capi, L, dev_index, n_rank, q, dev, call_images=1024):
+    """1080p RGB images -> .ric files -> images with the entropy stage on the device too (ric_compress_u8_gpu /
+    ric_decompress_u8_gpu): this rank's n_rank images in calls of at most `call_images`.  Pinned host buffers; H2D of
+    the pixels, all kernels, D2H of the finished files (and the reverse) inside the timed region.  Returns this
+    rank's seconds; the caller aggregates over ranks."""
     import numpy as np
     from rududu_image_codec_b200.synth import synth_image
     w, h, ch, distinct = 1920, 1080, 3, 8
     img_px = w * h * ch
     stride = img_px // 4 + 4096
-    ctx = capi.Context(w, h, ch, LEVELS_, max_batch=n, device=dev_index)
-    h_src, p1 = pinned_array(L, n * img_px)
-    h_dst, p2 = pinned_array(L, n * img_px)
-    h_files, p3 = pinned_array(L, n * stride)
-    sizes = np.zeros(n, dtype=np.uint64)
+    m = min(call_images, n_rank)
+    calls = (n_rank + m - 1) // m
+    ctx = capi.Context(w, h, ch, LEVELS_, max_batch=m, device=dev_index)
+    h_src, p1 = pinned_array(L, m * img_px)
+    h_dst, p2 = pinned_array(L, m * img_px)
+    h_files, p3 = pinned_array(L, m * stride)
+    sizes = np.zeros(m, dtype=np.uint64)
     base = np.stack([synth_image(100 + i, w, h, ch) for i in range(distinct)]).reshape(distinct, -1)
-    v = h_src.reshape(n, img_px)
-    for i in range(n):
+    v = h_src.reshape(m, img_px)
+    for i in range(m):
         v[i] = base[i % distinct]
-
-    def check(rc):
-        if rc:
-            raise RuntimeError(L.ric_last_error().decode())
-    out = {"api": "ric_compress_u8_gpu / ric_decompress_u8_gpu (entropy stage on the device, one image per warp)",
-           "workload": "%d images of %dx%d RGB, q=%d (BASELINE configs[3] shape)" % (n, w, h, q), "images": n}
+    out = {"images_this_rank": n_rank, "images_per_call": m}
     try:
-        check(L.ric_compress_u8_gpu(ctx.h, h_src.ctypes.data, n, q, h_files.ctypes.data, stride, sizes.ctypes.data))  # warm-up
+        _check(L, L.ric_compress_u8_gpu(ctx.h, h_src.ctypes.data, m, q, h_files.ctypes.data, stride, sizes.ctypes.data))  # warm-up
         t0 = time.perf_counter()
-        check(L.ric_compress_u8_gpu(ctx.h, h_src.ctypes.data, n, q, h_files.ctypes.data, stride, sizes.ctypes.data))
+        for _ in range(calls):
+            _check(L, L.ric_compress_u8_gpu(ctx.h, h_src.ctypes.data, m, q, h_files.ctypes.data, stride, sizes.ctypes.data))
         t1 = time.perf_counter()
-        check(L.ric_decompress_u8_gpu(ctx.h, h_files.ctypes.data, stride, sizes.ctypes.data, n, h_dst.ctypes.data))  # warm-up
+        _check(L, L.ric_decompress_u8_gpu(ctx.h, h_files.ctypes.data, stride, sizes.ctypes.data, m, h_dst.ctypes.data))  # warm-up
         t2 = time.perf_counter()
-        check(L.ric_decompress_u8_gpu(ctx.h, h_files.ctypes.data, stride, sizes.ctypes.data, n, h_dst.ctypes.data))
+        for _ in range(calls):
+            _check(L, L.ric_decompress_u8_gpu(ctx.h, h_files.ctypes.data, stride, sizes.ctypes.data, m, h_dst.ctypes.data))
         t3 = time.perf_counter()
         # one image through the host entropy stage must give the same file (the device runs the same coder source)
         one = capi.Context(w, h, ch, LEVELS_, device=dev_index)
         ref_file = one.compress_u8(base[1].reshape(1, ch, h, w), q, threads=1)[0]
         one.close()
-        got = h_files.reshape(n, stride)[1, :int(sizes[1])].tobytes()
-        out.update({"compress_mpix_s": n * w * h / (t1 - t0) / 1e6, "decompress_mpix_s": n * w * h / (t3 - t2) / 1e6,
-                    "mean_file_bytes": float(sizes.mean()), "h2d_bytes": n * img_px, "d2h_bytes": int(sizes.sum()),
+        got = h_files.reshape(m, stride)[1, :int(sizes[1])].tobytes()
+        out.update({"compress_s": t1 - t0, "decompress_s": t3 - t2, "pixels": calls * m * w * h,
+                    "mean_file_bytes": float(sizes.mean()), "h2d_bytes": calls * m * img_px, "d2h_bytes": calls * int(sizes.sum()),
                     "file_equals_host_entropy_path": got == ref_file})
     finally:
         ctx.close()
         for p in (p1, p2, p3):
             L.ric_host_free(p)
+    return out
+
+
+def configs3_figures(capi, L, args, rank, world, local, dev, max_over_ranks):
+    """BASELINE configs[3]: a batch of `--configs3-images` synthetic 1920x1080 RGB images STRONG-scaled over the
+    ranks (contiguous slices, no collective).  Three figures per run, every rank working on its slice:
+    the device-resident encode+decode stage, whole .ric files with the entropy stage on the device, and whole .ric
+    files with the host entropy threads overlapped (ric_compress_u8; a bounded sample of the slice, the host
+    threads of the box divided among the ranks)."""
+    import numpy as np
+    import torch
+    from rududu_image_codec_b200.sharding import shard
+    from rududu_image_codec_b200.synth import synth_batch_torch
+    w, h, ch, q = 1920, 1080, 3, args.q
+    G = args.configs3_images
+    b, e = shard(G, rank, world)
+    n_rank = e - b
+    px = w * h
+    out = {"workload": "%d images of %dx%d RGB, q=%d, 5-level cdf97, global batch sharded over %d GPU(s)" % (G, w, h, q, world),
+           "scaling": "strong", "images_per_gpu": (G + world - 1) // world}
+    # (a) device-resident stage, chunks of at most 512 images
+    m = min(512, n_rank)
+    chunks = (n_rank + m - 1) // m
+    ctx = capi.Context(w, h, ch, LEVELS_, max_batch=m, device=local)
+    distinct = min(m, 8)
+    imgs = synth_batch_torch(b, distinct, w, h, ch, dev)
+    src = imgs[torch.arange(m, device=dev) % distinct].contiguous()
+    ar = torch.zeros(m * ctx.image_arena_bytes + 64, dtype=torch.uint8, device=dev)
+    dst = torch.zeros_like(src)
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.encode_u8_device(src.data_ptr(), w, m, q, ar.data_ptr(), st)
+    torch.cuda.synchronize()
+    dec = ar.clone()
+    unfold_arenas_(ctx, dec, distinct)
+    per = ctx.image_arena_bytes
+    for i in range(distinct, m):
+        dec[i * per:(i + 1) * per].copy_(dec[(i % distinct) * per:((i % distinct) + 1) * per])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for timed in (False, True):
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(chunks):
+            ctx.encode_u8_device(src.data_ptr(), w, m, q, ar.data_ptr(), st)
+            ctx.decode_u8_device(dec.data_ptr(), m, q, dst.data_ptr(), w, st)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    out["stage_mpix_s"] = 2.0 * G * px / (ms * 1e-3) / 1e6
+    out["stage_ms"] = ms
+    # (c) host entropy overlapped: bounded sample of the slice through ric_compress_u8 / ric_decompress_u8
+    threads = max(1, (os.cpu_count() or 1) // world)
+    ns = min(m, 16 * threads)
+    h_src, p1 = pinned_array(L, ns * px * ch)
+    h_dst, p2 = pinned_array(L, ns * px * ch)
+    h_src[:] = src[:ns].reshape(-1).cpu().numpy()
+    stride = px * ch + 4096
+    files = np.empty(ns * stride, dtype=np.uint8)
+    sizes = np.zeros(ns, dtype=np.uint64)
+    try:
+        _check(L, L.ric_compress_u8(ctx.h, h_src.ctypes.data, ns, q, files.ctypes.data, stride, sizes.ctypes.data, threads))  # warm-up
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        _check(L, L.ric_compress_u8(ctx.h, h_src.ctypes.data, ns, q, files.ctypes.data, stride, sizes.ctypes.data, threads))
+        t1 = time.perf_counter()
+        _check(L, L.ric_decompress_u8(ctx.h, files.ctypes.data, stride, sizes.ctypes.data, ns, h_dst.ctypes.data, threads))
+        t2 = time.perf_counter()
+        tc, td = max_over_ranks(t1 - t0, dev), max_over_ranks(t2 - t1, dev)
+        out["files_host_entropy"] = {
+            "api": "ric_compress_u8 / ric_decompress_u8: GPU stage chunk-pipelined with the host entropy threads",
+            "sample": "%d images per rank (bounded sample of its %d), %d host threads per rank" % (ns, n_rank, threads),
+            "compress_mpix_s": world * ns * px / tc / 1e6, "decompress_mpix_s": world * ns * px / td / 1e6,
+            "round_trip_equals_decode_stage": bool(np.array_equal(h_dst[:px * ch], dst[0].reshape(-1).cpu().numpy()))}
+    finally:
+        L.ric_host_free(p1)
+        L.ric_host_free(p2)
+    del src, ar, dec, dst
+    ctx.close()
+    torch.cuda.empty_cache()
+    # (b) whole files, entropy stage on the device
+    f = ric_file_throughput_device(capi, L, local, n_rank, q, dev)
+    tc, td = max_over_ranks(f["compress_s"], dev), max_over_ranks(f["decompress_s"], dev)
+    tot_px = max_over_ranks(float(f["pixels"]), dev) * world  # (slices differ by at most one image)
+    out["files_device_entropy"] = {
+        "api": "ric_compress_u8_gpu / ric_decompress_u8_gpu (pixels up, finished files down; arenas stay in HBM)",
+        "images_per_call": f["images_per_call"], "compress_mpix_s": tot_px / tc / 1e6, "decompress_mpix_s": tot_px / td / 1e6,
+        "mean_file_bytes": f["mean_file_bytes"], "h2d_bytes_per_gpu": f["h2d_bytes"], "d2h_bytes_per_gpu": f["d2h_bytes"],
+        "file_equals_host_entropy_path": f["file_equals_host_entropy_path"]}
+    return out
+
+
+def copy_only_roof(torch, dev, pairs, steps, max_over_ranks):
+    """The box's own roof for the e2e path: the same pinned H2D and D2H copies per step, on two streams, no kernels."""
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def go():
+        for kind, dst, src in pairs:
+            with torch.cuda.stream(s1 if kind == "h2d" else s2):
+                dst.copy_(src, non_blocking=True)
+    go()
+    torch.cuda.synchronize()
+    if torch.distributed.is_initialized():
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        go()
+    torch.cuda.synchronize()
+    return max_over_ranks(time.perf_counter() - t0, dev)
+
+
+def class_api_figure(capi, dev_index, q, with_reference):
+    """The literal drop-in path (include/rududu_b200/wavelet2d.h drives exactly these calls): per plane of ONE
+    4K RGB image, CWavelet2D::Transform (ric_transform: plane up, level kernels, raw bands down) then CodeBand
+    (ric_quant: quantiser kernels on the resident bands, quantised arena down; then the host entropy stage)."""
+    import numpy as np
+    from rududu_image_codec_b200.synth import synth_image
+    img = synth_image(0, W_, H_, CH_).astype(np.int16)
+    co = img[0] - img[2]
+    t = img[2] + (co >> 1)
+    cg = img[1] - t
+    y = t + (cg >> 1) - 128
+    planes = [np.ascontiguousarray(co << 3), np.ascontiguousarray(cg << 3), np.ascontiguousarray(y << 4)]  # ric.cpp:76-91
+    c = capi.Context(W_, H_, 1, LEVELS_, device=dev_index)
+    tt = tq = te = 0.0
+    nbytes = 0
+    try:
+        for rep in range(3):
+            stream = np.zeros(W_ * H_ * CH_ * 2 + 4096, dtype=np.uint8)
+            mux = capi.Mux(stream, encode=True)
+            tt = tq = te = 0.0
+            for p in (2, 1, 0):  # ric.cpp:163-168
+                Q, lam = capi.plane_quant(q, CH_, p)
+                t0 = time.perf_counter()
+                c.transform(planes[p])
+                t1 = time.perf_counter()
+                a = c.quant(Q, lam)
+                t2 = time.perf_counter()
+                mux.code_plane(W_, H_, a)
+                t3 = time.perf_counter()
+                tt, tq, te = tt + t1 - t0, tq + t2 - t1, te + t3 - t2
+            nbytes = mux.finish()
+            mux.close()
+    finally:
+        c.close()
+    out = {"api": "per plane: ric_transform + ric_quant (host buffers in and out, blocking) + ric_mux_code_plane (one host thread)",
+           "image": "%dx%d RGB, q=%d" % (W_, H_, q), "transform_ms": tt * 1e3, "quant_ms": tq * 1e3, "entropy_ms": te * 1e3,
+           "transform_quant_mpix_s": W_ * H_ / (tt + tq) / 1e6, "whole_image_mpix_s": W_ * H_ / (tt + tq + te) / 1e6,
+           "payload_bytes": int(nbytes)}
+    if with_reference:
+        r = cpu_reference_stage(1, 1, q)
+        if r is not None:
+            out["reference_cpu_transform_quant_mpix_s"] = W_ * H_ / r[0] / 1e6
+            out["reference_cpu_note"] = "Transform + CodeBand's quantiser half of the compiled reference, one host thread, same image"
     return out
 
 
@@ -317,7 +488,7 @@ def run_ours(args):
     import torch.distributed as dist
     from rududu_image_codec_b200 import capi
     from rududu_image_codec_b200.sharding import max_over_ranks, shard
-    from rududu_image_codec_b200.synth import synth_image
+    from rududu_image_codec_b200.synth import synth_batch_torch, synth_image
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
@@ -338,11 +509,8 @@ def run_ours(args):
 
     ctx = capi.Context(W_, H_, CH_, LEVELS_, max_batch=B, device=local)
     pitch = W_  # multiple of 8: dense rows
-    distinct = min(B, 4)
     first, _ = shard(world * B, rank, world)  # this rank's slice of the global batch (weak scaling: B each)
-    host_imgs = np.stack([synth_image(first + i, W_, H_, CH_) for i in range(distinct)])
-    host_batch = np.ascontiguousarray(host_imgs[np.arange(B) % distinct])
-    src = torch.from_numpy(host_batch).to(dev)
+    src = torch.cat([synth_batch_torch(first + i, min(4, B - i), W_, H_, CH_, dev) for i in range(0, B, 4)])  # B distinct images
     arenas = torch.zeros(B * ctx.image_arena_bytes + 64, dtype=torch.uint8, device=dev)
     dec_in = torch.zeros_like(arenas)
     dst = torch.zeros((B, CH_, H_, pitch), dtype=torch.uint8, device=dev)
@@ -356,10 +524,7 @@ def run_ours(args):
     ctx.encode_u8_device(src.data_ptr(), pitch, B, q, arenas.data_ptr(), st)
     torch.cuda.synchronize()
     dec_in.copy_(arenas)
-    unfold_arenas_(ctx, dec_in, distinct)
-    per = ctx.image_arena_bytes
-    for i in range(distinct, B):
-        dec_in[i * per:(i + 1) * per].copy_(dec_in[(i % distinct) * per:((i % distinct) + 1) * per])
+    unfold_arenas_(ctx, dec_in, B)
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -371,8 +536,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     ctx.set_profiling(True)
-    e0, e1, em = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    enc_ms = dec_ms = 0.0
+    e0, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(2))
     barrier()
     sampler.start()
     e0.record()
@@ -384,6 +548,7 @@ def run_ours(args):
     total_ms = e0.elapsed_time(e1)
     lt_enc, lt_dec = ctx.level_times(0), ctx.level_times(1)  # last timed step, per launch
     enc_ms, dec_ms = sum(lt_enc), sum(lt_dec)
+    path_stats = ctx.path_stats()
     ctx.set_profiling(False)
     sampler.join(timeout=2)
 
@@ -393,12 +558,13 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer C ABI calls (pinned host memory, copies inside) ----
     L = capi.lib()
-    h_src, p1 = pinned_array(L, host_batch.nbytes)
-    h_ar, p2 = pinned_array(L, B * ctx.image_arena_bytes)
-    h_dec_in, p3 = pinned_array(L, B * ctx.image_arena_bytes)
-    h_dst, p4 = pinned_array(L, host_batch.nbytes)
-    h_src[:] = host_batch.reshape(-1)
-    h_dec_in[:] = dec_in[:B * ctx.image_arena_bytes].cpu().numpy()
+    nb_px, nb_ar = B * CH_ * H_ * W_, B * ctx.image_arena_bytes
+    h_src, p1 = pinned_array(L, nb_px)
+    h_ar, p2 = pinned_array(L, nb_ar)
+    h_dec_in, p3 = pinned_array(L, nb_ar)
+    h_dst, p4 = pinned_array(L, nb_px)
+    h_src[:] = src.reshape(-1).cpu().numpy()
+    h_dec_in[:] = dec_in[:nb_ar].cpu().numpy()
     ctx.encode_u8(h_src, q, out=h_ar)
     ctx.decode_u8(h_dec_in, B, q, out=h_dst)
     barrier()
@@ -418,8 +584,7 @@ def run_ours(args):
         rc = L.ric_encode_u8_stream(ctx.h, h_src.ctypes.data, B, q, h_ar.ctypes.data, null_cb, None)
         rc = rc or L.ric_decode_u8_stream(ctx_d.h, h_dec_in.ctypes.data, B, q, h_dst.ctypes.data, null_cb, None)
         rc = rc or L.ric_sync(ctx.h) or L.ric_sync(ctx_d.h)
-        if rc:
-            raise RuntimeError(L.ric_last_error().decode())
+        _check(L, rc)
     duplex_step()
     barrier()
     t0 = time.perf_counter()
@@ -429,8 +594,23 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     e2e_val = 2.0 * pixels_per_step * args.e2e_steps / max_over_ranks(e2e_s, dev) / 1e6
     ctx_d.close()
-    h2d = host_batch.nbytes + B * ctx.image_arena_bytes
-    d2h = B * ctx.image_arena_bytes + host_batch.nbytes
+    h2d = nb_px + nb_ar
+    d2h = nb_ar + nb_px
+    # the box's roof for exactly these copies (no kernels): what e2e could reach if the GPU work were free
+    tH = [torch.from_numpy(a) for a in (h_src, h_dec_in, h_ar, h_dst)]
+    roof_s = copy_only_roof(torch, dev, [("h2d", src.view(-1), tH[0]), ("h2d", dec_in[:nb_ar], tH[1]),
+                                         ("d2h", tH[2], arenas[:nb_ar]), ("d2h", tH[3], dst.view(-1))],
+                            args.e2e_steps, max_over_ranks)
+    copy_roof_val = 2.0 * pixels_per_step * args.e2e_steps / roof_s / 1e6
+
+    extras = {}
+    if args.configs3_images > 0:  # every rank takes part (strong scaling); rank 0 reports
+        del dst
+        torch.cuda.empty_cache()
+        try:
+            extras["configs3"] = configs3_figures(capi, L, args, rank, world, local, dev, max_over_ranks)
+        except Exception as e:  # secondary figures must not take the headline line down with them
+            extras["configs3"] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -441,11 +621,7 @@ def run_ours(args):
             "metric": "encode+decode transform+quant stage throughput", "value": value, "unit": "Mpixel/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": "%dx%d RGB (BASELINE configs[%d] shape), 5-level cdf97, q=%d, batch %d images per GPU, "
-                                   "encode stage + decode stage per step" % (W_, H_, 1 if W_ == 3840 else 3, q, B),
-                       "batch_per_gpu": B, "distinct_images_per_gpu": distinct,
-                       "l2": "inputs larger than L2 (%.0f MB read+written per step)" % ((h2d + d2h) / 1e6),
-                       "sharding": "independent images per rank, no collective"},
+            "config": workload_config(args),
             "encode_mpix_s": world * B * W_ * H_ / (enc_ms * 1e-3) / 1e6,
             "decode_mpix_s": world * B * W_ * H_ / (dec_ms * 1e-3) / 1e6,
             "stage": {"encode_ms": enc_ms, "decode_ms": dec_ms,
@@ -453,8 +629,10 @@ def run_ours(args):
                       "decode_alg_gbs": ALG_BYTES_PER_SAMPLE * S / (dec_ms * 1e-3) / 1e9,
                       "encode_frac": ALG_BYTES_PER_SAMPLE * S / (enc_ms * 1e-3) / 1e9 / peak,
                       "decode_frac": ALG_BYTES_PER_SAMPLE * S / (dec_ms * 1e-3) / 1e9 / peak,
-                      "level_ms_encode": lt_enc, "level_ms_decode": lt_dec},
-            "roofline": {"bound": "hbm", "kernel": "fwd_level_kernel<short, cdf97, SRC_U8_RGB> (level 0)",
+                      "level_ms_encode": lt_enc, "level_ms_decode": lt_dec,
+                      "inv_level0_frac": L0_INV_BYTES_PER_SAMPLE * S / (lt_dec[-1] * 1e-3) / 1e9 / peak,
+                      "packed_path_stats": path_stats},
+            "roofline": {"bound": "hbm", "kernel": "level-0 forward kernel (colour + 9/7 level + encode quantiser)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": L0_FWD_BYTES_PER_SAMPLE * S},
@@ -463,10 +641,15 @@ def run_ours(args):
                     "api": "ric_encode_u8_stream + ric_decode_u8_stream on two contexts, then ric_sync (pinned host buffers; "
                            "both PCIe directions busy at once)",
                     "sequential_value": e2e_seq_val,
-                    "sequential_api": "ric_encode_u8 then ric_decode_u8, blocking, one context"},
+                    "sequential_api": "ric_encode_u8 then ric_decode_u8, blocking, one context",
+                    "copy_only_value": copy_roof_val,
+                    "copy_only_gbs_each_way": h2d * args.e2e_steps * world / roof_s / 1e9,
+                    "copy_only_note": "the same pinned H2D + D2H copies per step on two streams with no kernels at all, all ranks "
+                                      "at once: the box's PCIe / host-memory roof for this path"},
             "gpu_launches": 2 * ctx.nlev * args.steps,
             "clocks": sampler.result(),
         }
+        line.update(extras)
         traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(traffic_file) and W_ == 3840:
             try:
@@ -478,22 +661,23 @@ def run_ours(args):
                 if "fwd_level0_issue_active_pct" in tj:  # the roof this kernel actually sits under (ncu, same workload)
                     line["roofline"]["issue_slot_frac"] = tj["fwd_level0_issue_active_pct"] / 100.0
                     line["roofline"]["alu_pipe_frac"] = tj["fwd_level0_alu_pipe_pct"] / 100.0
+                if "fwd_level0_thread_inst_per_sample" in tj:
+                    line["roofline"]["thread_inst_per_sample"] = tj["fwd_level0_thread_inst_per_sample"]
             except Exception:
                 pass
-        if world == 1:  # the single-image shapes of BASELINE configs[1] and [2] (latency-bound: 5 dependent launches)
+        if world == 1:  # the single-image shapes of BASELINE configs[1] and [2]
             line["single_image"] = {
                 "3840x2160x3_L5": single_image_latency(capi, synth_image, dev, 3840, 2160, CH_, LEVELS_, q),
                 "8192x8192x1_L6": single_image_latency(capi, synth_image, dev, 8192, 8192, 1, 6, q)}
         if world == 1:  # whole .ric files: the GPU stage feeding the host entropy stage (SURVEY 8d "separately an e2e number ...")
             try:
                 line["ric_files"] = ric_file_throughput(L, ctx, h_src, h_dst, B, q, not args.no_cpu_baseline)
-            except Exception as e:  # secondary figures must not take the headline line down with them
-                line["ric_files"] = {"error": str(e)}
-        if world == 1 and args.files_batch > 0:
-            try:
-                line["ric_files_device"] = ric_file_throughput_device(capi, L, local, args.files_batch, q)
             except Exception as e:
-                line["ric_files_device"] = {"error": str(e)}
+                line["ric_files"] = {"error": str(e)}
+            try:
+                line["class_api"] = class_api_figure(capi, local, q, not args.no_cpu_baseline)
+            except Exception as e:
+                line["class_api"] = {"error": str(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             r = cpu_reference_stage(threads, threads, q)
@@ -510,6 +694,7 @@ def run_ours(args):
         L.ric_host_free(p)
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

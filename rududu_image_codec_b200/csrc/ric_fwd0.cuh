@@ -268,6 +268,9 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 				const uint4 a = sm.stage[p][0][lane], b = sm.stage[p][1][lane];
 				X[0] = a.x; X[1] = a.y; X[2] = a.z; X[3] = a.w; X[4] = b.x; X[5] = b.y; X[6] = b.z; X[7] = b.w;
 			}
+			// the plane's pipeline state is fetched now, so that the row pass hides the shared-memory latency
+			uint4 *st = &sm.state[p][0][lane];
+			const uint4 q0 = st[0], q1 = st[32], q2 = st[64], q3 = st[96];
 			if (EDGE) {  // warp-uniform; a copy goes through the call so that X itself stays in registers
 				unsigned Y[8];
 #pragma unroll
@@ -287,11 +290,9 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 			NE[2] = prmt(X[1], X[3], 0x5410u) + (KV::E0 - KH::O4); NO[2] = prmt(X[1], X[3], 0x7632u) + (KV::O0 - KH::O4);
 			NE[3] = prmt(X[5], X[7], 0x5410u) + (KV::E0 - KH::O4); NO[3] = prmt(X[5], X[7], 0x7632u) + (KV::O0 - KH::O4);
 
-			uint4 *st = &sm.state[p][0][lane];
 			unsigned E3[4], O4[4];  // finished even row 2t-2 / odd row 2t-3 as two's-complement pairs
 			bool fast = false;
 			unsigned E1[4];
-			const uint4 q0 = st[0], q1 = st[32];
 			const unsigned so1[4] = {q0.x, q0.y, q0.z, q0.w}, se1[4] = {q1.x, q1.y, q1.z, q1.w};
 			if (interior && ((state_ok >> p) & 1u)) {
 #pragma unroll
@@ -300,7 +301,6 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 				fast = __all_sync(FULL, (go | ge) == 0);
 			}
 			if (fast) {
-				const uint4 q2 = st[64], q3 = st[96];
 				const unsigned so2[4] = {q2.x, q2.y, q2.z, q2.w}, se3[4] = {q3.x, q3.y, q3.z, q3.w};
 				unsigned O2[4], E3k[4];
 #pragma unroll
