@@ -145,6 +145,39 @@ int ric_tsuq(ric_ctx *ctx, int Quant, float thres, void *arena, unsigned *count)
 int ric_tsuqi(ric_ctx *ctx, int Quant, void *arena);
 int ric_transform_inv(ric_ctx *ctx, const void *arena, int16_t *plane, int stride);
 
+/* ric_set_base_weight: the baseWeight argument of CWavelet2D::SetWeight(t, baseWeight) (wavelet2d.h:36,
+ * wavelet2d.cpp:1009-1032): the band weights of the context are recomputed in the reference's expression order
+ * (top level D = base / scale, V = H = base, L = base * scale, then down the chain).  1.0 at ric_create. */
+int ric_set_base_weight(ric_ctx *ctx, float baseWeight);
+/* ric_quant_host / ric_tsuq_host: like ric_quant / ric_tsuq, but on the bands in `arena` (HOST, in/out), which are
+ * uploaded first -- the reference's CodeBand / TSUQ work on pBand wherever the caller left it, so a caller that
+ * edits the bands between Transform() and CodeBand() needs this form.  The C++ shim always uses it. */
+int ric_quant_host(ric_ctx *ctx, int Quant, int lambda, void *arena);
+int ric_tsuq_host(ric_ctx *ctx, int Quant, float thres, void *arena, unsigned *count);
+
+/* ---- single bands, no context: the public per-band methods of the reference classes --------------------------
+ * A band is described the way CBand holds it (src/lib/band.h:43-59): `data` = pBand (HOST, in/out, rows of
+ * `stride` samples, short or int), dimx/dimy/stride = DimX/DimY/DimXAlign, weight = Weight.  Each call uploads
+ * the band(s), runs the kernel on `device` and downloads the result; these exist for API fidelity (the class
+ * shim's CBand::TSUQ / TSUQi / CBandCodec::buildTree call them), not for throughput.
+ * ric_buf_tsuq:   CBand::TSUQ<C>(Quant, Thres)   band.h:65-92;  count, min and max receive Count, Min and Max (each may be NULL).
+ * ric_buf_tsuqi:  CBand::TSUQi<C>(Quant)         band.h:94-107.
+ * ric_buf_build_tree: CBandCodec::buildTree<high_band, C>(Quant, lambda)  bandcodec.h:42, bandcodec.cpp:239-322
+ *   on chain[0] and then, as the reference recurses through pParent, on chain[1..n-1] (each the next coarser
+ *   band of the same orientation).  `flags` of every band (one byte per 4x4 block, ceil(dimx/4) per row) receives
+ *   "pRD != 0" -- the only thing the reference ever asks of pRD.  high_band == 0: chain[0] adds its child's blocks
+ *   like a parent band does; child_flags / child_dimx then describe that child (a previous call's output). */
+typedef struct ric_band_buf {
+	void *data;
+	int dimx, dimy, stride, is_int;
+	float weight;
+	unsigned char *flags; /* ric_buf_build_tree only: out, ceil(dimx/4) * ceil(dimy/4) bytes; may be NULL */
+} ric_band_buf;
+int ric_buf_tsuq(int device, const ric_band_buf *band, int Quant, float thres, unsigned *count, int *min, int *max);
+int ric_buf_tsuqi(int device, const ric_band_buf *band, int Quant);
+int ric_buf_build_tree(int device, const ric_band_buf *chain, int n, int high_band, const unsigned char *child_flags,
+                       int child_dimx, int Quant, int lambda);
+
 /* ---- .ric container header (src/ric/ric.cpp:114-121,135,150-154,187-200) --------------------------
  * 9 bytes: "RUD2", u16 LE width, u16 LE height, one byte Quant:5 | Color:1 << 5 | Trans:2 << 6.
  * The payload that follows is the entropy coder's buffer from offset 2 (ric.cpp:176). */

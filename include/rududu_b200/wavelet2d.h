@@ -5,7 +5,8 @@
 //   enum trans / cmode                     src/lib/utils.h:27-28
 //   enum band_t, ALIGN                     src/lib/band.h:33-35
 //   class CBand (public fields)            src/lib/band.h:37-161
-//   class CBandCodec::buildTree            src/lib/bandcodec.h:42   (here: CWavelet2D::QuantBands)
+//   class CBandCodec::buildTree            src/lib/bandcodec.h:42   (per band, and CWavelet2D::QuantBands for a whole plane)
+//   CBand::Init / TSUQ<C> / TSUQi<C>       src/lib/band.h:61-107
 //   class CWavelet2D                       src/lib/wavelet2d.h:27-88
 //        CWavelet2D(x, y, level, level_chg, Align), SetWeight, Transform<short>, TransformI<short>,
 //        CodeBand, DecodeBand, TSUQ, TSUQi, public DBand/HBand/VBand/LBand, pLow/pHigh chain
@@ -50,7 +51,75 @@ public:
 	CBand *pParent = 0, *pChild = 0, *pNeighbor[3] = {0, 0, 0};
 	char *pBand = 0;  // points into the owning CWavelet2D's pinned arena
 	band_t type = sshort;
+	int device = 0;  // (not in the reference) the GPU the per-band methods run on
 
+	CBand() {}
+	~CBand() { release(); }
+	CBand(const CBand &) = delete;
+	CBand &operator=(const CBand &) = delete;
+
+	// band.cpp:51-65: a row-padded, 32-byte aligned buffer of its own (bands of a CWavelet2D live in its arena instead)
+	void Init(band_t t = sshort, unsigned int x = 0, unsigned int y = 0, int Align = ALIGN)
+	{
+		release();
+		type = t;
+		DimX = x; DimY = y;
+		const unsigned sz = t == sint ? 4 : 2;
+		DimXAlign = ((x * sz + Align - 1) & -Align) / sz;
+		BandSize = DimXAlign * y;
+		if (BandSize) {
+			void *p = 0;
+			if (ric_host_alloc(&p, (size_t)BandSize * sz) < 0) fail();
+			pBand = (char *)p;
+			own_ = true;
+		}
+	}
+
+	// band.h:65-92: dead-zone quantiser on pBand (wherever the caller left it), sets Count / Min / Max
+	template <class C>
+	unsigned int TSUQ(int Quant, float Thres)
+	{
+		check_type<C>();
+		const ric_band_buf b = buf();
+		unsigned n = 0;
+		if (ric_buf_tsuq(device, &b, Quant, Thres, &n, &Min, &Max) < 0) fail();
+		Count = n;
+		return n;
+	}
+	// band.h:94-107
+	template <class C>
+	void TSUQi(C Quant)
+	{
+		check_type<C>();
+		const ric_band_buf b = buf();
+		if (ric_buf_tsuqi(device, &b, (int)Quant) < 0) fail();
+	}
+
+	ric_band_buf buf(unsigned char *flags = 0) const
+	{
+		ric_band_buf b;
+		b.data = pBand; b.dimx = (int)DimX; b.dimy = (int)DimY; b.stride = (int)DimXAlign; b.is_int = type == sint;
+		b.weight = Weight; b.flags = flags;
+		return b;
+	}
+	void attach(char *p) { release(); pBand = p; }  // (CWavelet2D: the band lives in the plane's arena)
+
+protected:
+	template <class C>
+	void check_type() const
+	{
+		if ((sizeof(C) == 4) != (type == sint)) throw std::runtime_error("rududu_b200: sample type does not match the band's type");
+	}
+	static void fail() { throw std::runtime_error(std::string("rududu_b200: ") + ric_last_error()); }
+	void release()
+	{
+		if (own_ && pBand) ric_host_free(pBand);
+		pBand = 0;
+		own_ = false;
+	}
+	bool own_ = false;
+
+public:
 	// Host-side helpers of the reference class (band.h:114-159, band.cpp:162-167): statistics and debugging
 	// aids over the band buffer, not part of the hot path.
 	template <class C>
@@ -86,7 +155,33 @@ public:
 	}
 };
 
-typedef CBand CBandCodec;  // the entropy half lives in the reference; the data members are CBand's
+// CBandCodec: the quantiser half (buildTree, bandcodec.h:42, bandcodec.cpp:239-322).  The entropy half (pred / tree)
+// is this library's host entropy stage, reached through CWavelet2D::CodeBand / DecodeBand.
+class CBandCodec : public CBand {
+public:
+	CBandCodec() {}
+	~CBandCodec() { delete[] pRD; }
+
+	// Quantises this band and then, as the reference recurses through pParent, every coarser band of the chain.
+	// high_band: this band is the finest of its orientation (no children); otherwise its child's pRD -- left by an
+	// earlier buildTree on the child -- is added, as in the reference.  Works on pBand in host memory.
+	template <bool high_band, class C>
+	void buildTree(const C Quant, const int lambda)
+	{
+		check_type<C>();
+		ric_band_buf chain[RIC_MAX_LEVELS];
+		int n = 0;
+		for (CBandCodec *b = this; b && n < RIC_MAX_LEVELS; b = (CBandCodec *)b->pParent) {
+			if (!b->pRD) b->pRD = new unsigned char[((b->DimX + 3) / 4) * ((b->DimY + 3) / 4)];  // bandcodec.cpp:252-253
+			chain[n++] = b->buf(b->pRD);
+		}
+		const CBandCodec *ch = (const CBandCodec *)pChild;
+		if (!high_band && !(ch && ch->pRD)) throw std::runtime_error("rududu_b200: buildTree<false> needs the child's pRD (run buildTree on it first)");
+		if (ric_buf_build_tree(device, chain, n, high_band, high_band ? 0 : ch->pRD, high_band ? 0 : (int)ch->DimX, (int)Quant, lambda) < 0) fail();
+	}
+
+	unsigned char *pRD = 0;  // one byte per 4x4 block: the reference's pRD != 0 (all it ever asks of pRD)
+};
 
 // CMuxCodec as ric.cpp uses it: CMuxCodec(pStream, firstWord) to write, CMuxCodec(pStream) to read,
 // endCoding() (muxcodec.cpp:25-64,92-113).  The reference knows no buffer bounds; pass `capacity` when
@@ -131,15 +226,24 @@ public:
 	{
 		ctx_[0] = ctx_[1] = ctx_[2] = 0;
 		arena_ = 0;
-		ric_ctx *c = ctx(cdf97);
-		ric_info inf;
-		check(ric_get_info(c, &inf));
-		nlev_ = inf.nlev;
-		arena_bytes_ = inf.arena_bytes;
-		void *p = 0;
-		check(ric_host_alloc(&p, arena_bytes_));
-		arena_ = (char *)p;
-		build_chain(c);
+		try {
+			ric_ctx *c = ctx(cdf97);
+			ric_info inf;
+			check(ric_get_info(c, &inf));
+			nlev_ = inf.nlev;
+			arena_bytes_ = inf.arena_bytes;
+			void *p = 0;
+			check(ric_host_alloc(&p, arena_bytes_));
+			arena_ = (char *)p;
+			build_chain(c);
+		} catch (...) {  // a constructor that throws runs no destructor: release what exists
+			for (CWavelet2D *w = pLow; w;) { CWavelet2D *n = w->pLow; w->pLow = 0; delete w; w = n; }
+			pLow = 0;
+			if (arena_) ric_host_free(arena_);
+			for (int i = 0; i < 3; i++)
+				if (ctx_[i]) ric_destroy(ctx_[i]);
+			throw;
+		}
 	}
 	~CWavelet2D()
 	{
@@ -154,9 +258,9 @@ public:
 	// CWavelet2D::SetWeight, wavelet2d.cpp:1009-1032 (weights come from the C ABI's band table)
 	void SetWeight(trans t, float baseWeight = 1.f)
 	{
-		if (baseWeight != 1.f) throw std::runtime_error("rududu_b200: baseWeight != 1 unsupported");
 		trans_ = t;
 		ric_ctx *c = ctx(t);
+		check(ric_set_base_weight(c, baseWeight));
 		int id = 0;
 		for (CWavelet2D *w = this; w; w = w->pLow, id += 3) {
 			ric_band_info b;
@@ -187,9 +291,10 @@ public:
 	}
 
 	// The quantiser half of CodeBand (wavelet2d.cpp:110-126): buildTree on the D/H/V chains and
-	// TSUQ(Quant, 0.5) on the LL band, on the coefficients the last Transform() left on the GPU.
-	// Afterwards the bands hold exactly what CBandCodec::pred / tree<encode> expect.
-	void QuantBands(int Quant, int lambda) { check(ric_quant(ctx(trans_), Quant, lambda, arena_)); }
+	// TSUQ(Quant, 0.5) on the LL band, on the coefficients in the band buffers (host edits since Transform()
+	// included: the arena is uploaded first).  Afterwards the bands hold exactly what CBandCodec::pred /
+	// tree<encode> expect.
+	void QuantBands(int Quant, int lambda) { check(ric_quant_host(ctx(trans_), Quant, lambda, arena_)); }
 
 	// wavelet2d.cpp:83-159: quantiser half on the GPU, then the entropy half on the host into pCodec's stream.
 	void CodeBand(CMuxCodec *pCodec, int Quant, int lambda)
@@ -208,7 +313,7 @@ public:
 	unsigned int TSUQ(int Quant, float Thres)
 	{
 		unsigned n = 0;
-		check(ric_tsuq(ctx(trans_), Quant, Thres, arena_, &n));
+		check(ric_tsuq_host(ctx(trans_), Quant, Thres, arena_, &n));
 		return n;
 	}
 	void TSUQi(int Quant) { check(ric_tsuqi(ctx(trans_), Quant, arena_)); }
@@ -237,13 +342,14 @@ private:
 		return T->ctx_[t];
 	}
 
-	void fill(CBand &b, ric_ctx *c, int id)
+	void fill(CBandCodec &b, ric_ctx *c, int id)
 	{
 		ric_band_info i;
 		check(ric_get_band(c, id, &i));
 		b.DimX = i.dimx; b.DimY = i.dimy; b.DimXAlign = i.stride; b.BandSize = i.stride * i.dimy;
 		b.Weight = i.weight; b.type = i.is_int ? sint : sshort;
-		b.pBand = top()->arena_ + i.offset;
+		b.attach(top()->arena_ + i.offset);
+		b.device = top()->device_;
 	}
 
 	void build_chain(ric_ctx *c)

@@ -27,6 +27,7 @@ EXPORTS = [
     "ric_mux_encoder", "ric_mux_decoder", "ric_mux_code_plane", "ric_mux_decode_plane", "ric_mux_finish",
     "ric_mux_destroy", "ric_entropy_encode_device", "ric_entropy_decode_device",
     "ric_compress_u8_gpu", "ric_decompress_u8_gpu", "ric_entropy_encode_hinted",
+    "ric_set_base_weight", "ric_quant_host", "ric_tsuq_host", "ric_buf_tsuq", "ric_buf_tsuqi", "ric_buf_build_tree",
 ]
 
 

@@ -126,6 +126,7 @@ struct QuantLevelParams {
 	unsigned char *flags;
 	BandRef band[3], child[3];
 	int has_child, is_int;
+	int o_first;  // blockIdx.y + o_first = orientation (single-band launches of ric_buf_build_tree)
 	QuantBand qb[3];
 };
 
@@ -135,7 +136,7 @@ __global__ void quant_level_kernel(const __grid_constant__ QuantLevelParams P)
 	__shared__ QuantBand s_qb[3];
 	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
 	__syncthreads();
-	const int o = blockIdx.y;
+	const int o = blockIdx.y + P.o_first;
 	const BandRef &b = P.band[o];
 	const int nbx = b.fl_bw, nby = (b.dimy + 3) / 4;
 	const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,13 +174,15 @@ __global__ void quant_level_kernel(const __grid_constant__ QuantLevelParams P)
 	}
 }
 
-// mode 0: TSUQ (dead-zone quantise, count non-zeros); mode 1: TSUQi (multiply)
+// mode 0: TSUQ (dead-zone quantise, count non-zeros); mode 1: TSUQi (multiply).  count[0] += Count; count[1] /
+// count[2] (when count is given) = min / max of the quantised values over 0, as CBand::TSUQ keeps Min / Max.
 template <bool SH>
 __global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int dimy, int stride, int mode, int Q,
                                       int iQ, int T, unsigned *count)
 {
 	const long long n = (long long)dimx * dimy;
 	unsigned local = 0;
+	int lmin = 0, lmax = 0;
 	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
 		const int y = (int)(i / dimx), x = (int)(i % dimx);
 		char *p = arena + off + ((long long)y * stride + x) * (SH ? 2 : 4);
@@ -188,6 +191,8 @@ __global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int 
 			// Count counts every coefficient outside the dead zone (band.h:77-80), even if it rounds to 0
 			local += !((unsigned)(c + T) <= (unsigned)(2 * T));
 			c = tsuq1<SH>(c, T, iQ);
+			lmin = min(lmin, c);
+			lmax = max(lmax, c);
 		} else {
 			c = TR<SH>(c * Q);
 		}
@@ -195,7 +200,13 @@ __global__ void band_pointwise_kernel(char *arena, long long off, int dimx, int 
 	}
 	if (mode == 0 && count) {
 		local = __reduce_add_sync(0xffffffffu, local);
-		if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+		lmin = __reduce_min_sync(0xffffffffu, lmin);
+		lmax = __reduce_max_sync(0xffffffffu, lmax);
+		if ((threadIdx.x & 31) == 0) {
+			if (local) atomicAdd(count, local);
+			if (lmin < 0) atomicMin((int *)count + 1, lmin);
+			if (lmax > 0) atomicMax((int *)count + 2, lmax);
+		}
 	}
 }
 
@@ -366,7 +377,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 		CKD(cudaMalloc(&c->d_ll[i], bytes));
 		CKD(cudaMemset(c->d_ll[i], 0, bytes));
 	}
-	CKD(cudaMalloc(&c->d_count, sizeof(unsigned)));
+	CKD(cudaMalloc(&c->d_count, 4 * sizeof(unsigned)));
 	CKD(cudaMalloc(&c->d_stats, 8 * sizeof(unsigned long long)));
 	CKD(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
 	CKD(cudaMalloc(&c->d_jobctr, 4 * 2 * RIC_MAX_LEVELS * sizeof(unsigned long long)));
@@ -869,7 +880,7 @@ int ric_quant(ric_ctx *c, int Quant, int lambda, void *arena)
 static int pointwise_all(ric_ctx *c, char *d_arena, int mode, int Quant, float thres, unsigned *count)
 {
 	const HostGeom &g = c->g;
-	CK(cudaMemsetAsync(c->d_count, 0, sizeof(unsigned), c->stream));
+	CK(cudaMemsetAsync(c->d_count, 0, 4 * sizeof(unsigned), c->stream));
 	for (int id = 0; id < g.nbands; id++) {
 		const ric_band_info &b = g.band[id];
 		int Q = 1, iQ = 0, T = 0;
@@ -906,6 +917,163 @@ int ric_tsuqi(ric_ctx *c, int Quant, void *arena)
 	if (rc) return rc;
 	CK(cudaMemcpyAsync(arena, c->d_arena_in, c->g.arena_bytes, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
+	return RIC_OK;
+}
+
+int ric_set_base_weight(ric_ctx *c, float baseWeight)
+{
+	if (!c || !(baseWeight > 0.f)) return set_err(RIC_E_ARG, "ric_set_base_weight: bad argument");
+	HostGeom &g = c->g;
+	const float scale = g.trans == RIC_CDF97 ? 1.149604398f * 1.149604398f : 2.f;  // wavelet2d.cpp:1011-1016
+	float d = baseWeight / scale, v = baseWeight, l = baseWeight * scale;
+	for (int i = 0; i < g.nlev; i++) {
+		if (i > 0) { d = v; v = l; l = v * scale; }
+		g.band[3 * i + 0].weight = d;
+		g.band[3 * i + 1].weight = v;
+		g.band[3 * i + 2].weight = v;
+	}
+	g.band[3 * g.nlev].weight = l;
+	return RIC_OK;
+}
+
+int ric_quant_host(ric_ctx *c, int Quant, int lambda, void *arena)
+{
+	if (!c || !arena) return set_err(RIC_E_ARG, "ric_quant_host: null");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(c->d_arena, arena, c->g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
+	return ric_quant(c, Quant, lambda, arena);
+}
+
+int ric_tsuq_host(ric_ctx *c, int Quant, float thres, void *arena, unsigned *count)
+{
+	if (!c || !arena) return set_err(RIC_E_ARG, "ric_tsuq_host: null");
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(c->d_arena, arena, c->g.arena_bytes, cudaMemcpyHostToDevice, c->stream));
+	return ric_tsuq(c, Quant, thres, arena, count);
+}
+
+// ---- single bands without a context ------------------------------------------------------------------------
+
+static int buf_check(int device, const ric_band_buf *b, const char *who)
+{
+	if (!b || !b->data || b->dimx < 1 || b->dimy < 1 || b->stride < b->dimx || !(b->weight > 0.f))
+		return set_err(RIC_E_ARG, "%s: bad band description", who);
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return set_err(RIC_E_CUDA, "%s: no CUDA device (%s); this library has no CPU path", who, cudaGetErrorString(e));
+	if (device < 0 || device >= ndev) return set_err(RIC_E_ARG, "%s: bad device index", who);
+	CK(cudaSetDevice(device));
+	return RIC_OK;
+}
+
+static int buf_pointwise(int device, const ric_band_buf *b, int mode, int Quant, float thres, unsigned *count, int *mn, int *mx,
+                         const char *who)
+{
+	int rc = buf_check(device, b, who);
+	if (rc) return rc;
+	if (Quant < 0) return set_err(RIC_E_ARG, "%s: Quant < 0", who);
+	const size_t bytes = (size_t)b->stride * b->dimy * (b->is_int ? 4 : 2);
+	char *d = nullptr;
+	unsigned *dc = nullptr;
+	cudaError_t e = cudaMalloc(&d, bytes);
+	if (e == cudaSuccess) e = cudaMalloc(&dc, 4 * sizeof(unsigned));
+	if (e == cudaSuccess) e = cudaMemset(dc, 0, 4 * sizeof(unsigned));
+	if (e == cudaSuccess) e = cudaMemcpy(d, b->data, bytes, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		int Q = 1, iQ = 0, T = 0;
+		if (mode == 0) make_tsuq(Quant, thres, b->weight, b->is_int, &Q, &iQ, &T);
+		else Q = make_tsuqi(Quant, b->weight, b->is_int);
+		const int blocks = std::max(1, std::min(1024, (b->dimx * b->dimy + 1023) / 1024));
+		if (b->is_int) band_pointwise_kernel<false><<<blocks, 256>>>(d, 0, b->dimx, b->dimy, b->stride, mode, Q, iQ, T, dc);
+		else band_pointwise_kernel<true><<<blocks, 256>>>(d, 0, b->dimx, b->dimy, b->stride, mode, Q, iQ, T, dc);
+		e = cudaGetLastError();
+	}
+	unsigned hc[4] = {0, 0, 0, 0};
+	if (e == cudaSuccess) e = cudaMemcpy(b->data, d, bytes, cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess) e = cudaMemcpy(hc, dc, sizeof hc, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	cudaFree(dc);
+	if (e != cudaSuccess) return set_err(RIC_E_CUDA, "%s: %s", who, cudaGetErrorString(e));
+	if (count) *count = hc[0];
+	if (mn) *mn = (int)hc[1];
+	if (mx) *mx = (int)hc[2];
+	return RIC_OK;
+}
+
+int ric_buf_tsuq(int device, const ric_band_buf *band, int Quant, float thres, unsigned *count, int *mn, int *mx)
+{
+	return buf_pointwise(device, band, 0, Quant, thres, count, mn, mx, "ric_buf_tsuq");
+}
+
+int ric_buf_tsuqi(int device, const ric_band_buf *band, int Quant)
+{
+	return buf_pointwise(device, band, 1, Quant, 0.f, nullptr, nullptr, nullptr, "ric_buf_tsuqi");
+}
+
+int ric_buf_build_tree(int device, const ric_band_buf *chain, int n, int high_band, const unsigned char *child_flags,
+                       int child_dimx, int Quant, int lambda)
+{
+	if (n < 1 || n > RIC_MAX_LEVELS || Quant < 0 || lambda < 0 || (!high_band && (!child_flags || child_dimx < 1)))
+		return set_err(RIC_E_ARG, "ric_buf_build_tree: bad argument");
+	for (int i = 0; i < n; i++) {
+		int rc = buf_check(device, chain + i, "ric_buf_build_tree");
+		if (rc) return rc;
+		// a parent band is half its child in both directions (wavelet2d.cpp:73-79): the kernel indexes child blocks 2bx, 2by
+		if (i > 0 && (chain[i].dimx > (chain[i - 1].dimx + 1) / 2 + 1 || chain[i].dimy > (chain[i - 1].dimy + 1) / 2 + 1))
+			return set_err(RIC_E_ARG, "ric_buf_build_tree: chain[i] is not the next coarser band of chain[i-1]");
+	}
+	// one device block: [child flags][band 0][flags 0][band 1][flags 1]...
+	size_t off = 0, boff[RIC_MAX_LEVELS], foff[RIC_MAX_LEVELS], cf_off = 0;
+	const int child_bw = high_band ? 0 : (child_dimx + 3) / 4;
+	int fbw[RIC_MAX_LEVELS], fbh[RIC_MAX_LEVELS];
+	if (!high_band) {
+		fbw[0] = (chain[0].dimx + 3) / 4; fbh[0] = (chain[0].dimy + 3) / 4;
+		off = (((size_t)child_bw * (2 * fbh[0] + 2) + 2 * fbw[0] + 2) + 31) & ~(size_t)31;
+	}
+	for (int i = 0; i < n; i++) {
+		fbw[i] = (chain[i].dimx + 3) / 4; fbh[i] = (chain[i].dimy + 3) / 4;
+		boff[i] = off; off += (((size_t)chain[i].stride * chain[i].dimy * (chain[i].is_int ? 4 : 2)) + 31) & ~(size_t)31;
+		foff[i] = off; off += ((size_t)fbw[i] * fbh[i] + 64 + 31) & ~(size_t)31;
+	}
+	char *d = nullptr;
+	cudaError_t e = cudaMalloc(&d, off + 64);
+	if (e == cudaSuccess) e = cudaMemset(d, 0, off + 64);
+	if (e == cudaSuccess && !high_band) {
+		// only the rows / columns the band's full blocks look at need to exist; the caller's array covers them
+		const size_t need = (size_t)child_bw * std::min(2 * fbh[0], (chain[0].dimy / 4) * 2);
+		e = cudaMemcpy(d + cf_off, child_flags, need, cudaMemcpyHostToDevice);
+	}
+	for (int i = 0; i < n && e == cudaSuccess; i++)
+		e = cudaMemcpy(d + boff[i], chain[i].data, (size_t)chain[i].stride * chain[i].dimy * (chain[i].is_int ? 4 : 2), cudaMemcpyHostToDevice);
+	for (int i = 0; i < n && e == cudaSuccess; i++) {
+		QuantLevelParams P;
+		memset(&P, 0, sizeof P);
+		P.arena = d;
+		P.flags = (unsigned char *)d;
+		P.has_child = i > 0 || !high_band;
+		P.is_int = chain[i].is_int;
+		P.o_first = 0;
+		BandRef &b = P.band[0];
+		b.off = (long long)boff[i]; b.dimx = chain[i].dimx; b.dimy = chain[i].dimy; b.stride = chain[i].stride;
+		b.fl_off = (int)foff[i]; b.fl_bw = fbw[i];
+		if (P.has_child) {
+			BandRef &ch = P.child[0];
+			ch.fl_off = i > 0 ? (int)foff[i - 1] : (int)cf_off;
+			ch.fl_bw = i > 0 ? fbw[i - 1] : child_bw;
+		}
+		fill_qb(P.qb[0], Quant, lambda, chain[i].weight, chain[i].is_int);
+		dim3 grid((fbw[i] * fbh[i] + 127) / 128, 1);
+		if (chain[i].is_int) quant_level_kernel<false><<<grid, 128>>>(P);
+		else quant_level_kernel<true><<<grid, 128>>>(P);
+		e = cudaGetLastError();
+	}
+	for (int i = 0; i < n && e == cudaSuccess; i++) {
+		e = cudaMemcpy(chain[i].data, d + boff[i], (size_t)chain[i].stride * chain[i].dimy * (chain[i].is_int ? 4 : 2), cudaMemcpyDeviceToHost);
+		if (e == cudaSuccess && chain[i].flags) e = cudaMemcpy(chain[i].flags, d + foff[i], (size_t)fbw[i] * fbh[i], cudaMemcpyDeviceToHost);
+	}
+	cudaFree(d);
+	if (e != cudaSuccess) return set_err(RIC_E_CUDA, "ric_buf_build_tree: %s", cudaGetErrorString(e));
 	return RIC_OK;
 }
 

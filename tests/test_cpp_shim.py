@@ -101,3 +101,43 @@ def test_streaming_pipeline_with_reference_entropy_coder(tmp_path):
     r = subprocess.run([exe, str(w), str(h), str(n), str(q), str(tmp_path / "imgs.u8")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("ok")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,levels", [(512, 384, 5), (517, 389, 5), (130, 70, 2)])
+def test_per_band_methods_match_oracle(tmp_path, w, h, levels):
+    """CBandCodec::buildTree<high_band, C>, CBand::TSUQ<C> / TSUQi<C> / Init and SetWeight(t, baseWeight) of the shim
+    (src/lib/bandcodec.h:42, src/lib/band.h:61-107, src/lib/wavelet2d.h:36), called band by band the way
+    CWavelet2D::CodeBand / TSUQ / TSUQi call them, against the oracle's whole-plane functions."""
+    exe = _build(tmp_path, "band_api_test")
+    q = 9
+    plane = oraclebind.colour_fwd(synth_image(4, w, h, 1), q)[0]
+    Quant, lam = oraclebind.plane_quant(q, 1, 0)
+    o = oraclebind.Oracle(w, h, levels)
+    raw = o.forward(plane)
+    want_bt = raw.copy()
+    o.quant(want_bt, Quant, lam)
+    signed = want_bt.copy()
+    o.unfold(signed)
+    plane.tofile(tmp_path / "plane.s16")
+    signed.tofile(tmp_path / "signed.bin")
+    pre = str(tmp_path / "o_")
+    r = subprocess.run([exe, str(w), str(h), str(levels), str(Quant), str(lam), str(tmp_path / "plane.s16"),
+                        str(tmp_path / "signed.bin"), pre], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = dict(l.split(None, 1) for l in r.stdout.strip().splitlines() if " " in l)
+    rd = lambda name: np.fromfile(pre + name + ".bin", dtype=np.uint8)
+    assert np.array_equal(rd("bt"), want_bt)
+    ll = o.band_view(want_bt, o.nbands - 1)[:, :o.info(o.nbands - 1)["dimx"]]
+    f = out["ll_count"].split()
+    assert (int(f[2]), int(f[4])) == (min(int(ll.min()), 0), max(int(ll.max()), 0))
+    want_t = raw.copy()
+    n = o.tsuq_all(want_t, Quant, 0.7)
+    assert np.array_equal(rd("tsuq"), want_t)
+    assert int(out["tsuq_count"].split()[0]) == n
+    want_i = signed.copy()
+    o.tsuqi(want_i, Quant)
+    assert np.array_equal(rd("tsuqi"), want_i)
+    want_bw = raw.copy()
+    o.quant(want_bw, 2 * Quant, 2 * lam)  # every weight halved == Quant and lambda doubled (powers of two are exact in float)
+    assert np.array_equal(rd("bw"), want_bw)
