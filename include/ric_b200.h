@@ -238,8 +238,12 @@ int ric_mux_destroy(ric_mux *mux);
  * payload lengths (encode writes -1 where `stride` was too small).  Asynchronous on `stream`. */
 int ric_entropy_encode_device(ric_ctx *ctx, void *d_arenas, int n, uint8_t *d_out, size_t stride, long long *d_sizes,
                               void *stream);
+/* d_status (device, n ints, may be NULL): 0 where image i decoded cleanly, 1 where its payload was truncated or
+ * corrupt (the reader ran past the end, or met a code no encoder writes) or d_sizes[i] is negative / larger than
+ * `stride` -- such an image's arenas hold garbage (or stay cleared) and must not be used.  Without d_status a
+ * caller has no way to learn of a bad payload from this call; ric_decompress_u8_gpu checks internally. */
 int ric_entropy_decode_device(ric_ctx *ctx, const uint8_t *d_payloads, size_t stride, const long long *d_sizes, int n,
-                              void *d_arenas, void *stream);
+                              void *d_arenas, int *d_status, void *stream);
 
 /* ---- whole .ric files, batch (CompressImage / DecompressImage without the image-file I/O, ric.cpp:123-251) --
  * ric_compress_u8: n planar u8 images -> n complete .ric files (header + payload), file i at files + i*stride,

@@ -95,7 +95,7 @@ def lib():
         L.ric_entropy_encode_hinted.argtypes = [i] * 6 + [vp, vp, sz, C.POINTER(sz)]
         L.ric_compress_u8.argtypes = [vp, vp, i, i, vp, sz, vp, i]
         L.ric_entropy_encode_device.argtypes = [vp, vp, i, vp, sz, vp, vp]
-        L.ric_entropy_decode_device.argtypes = [vp, vp, sz, vp, i, vp, vp]
+        L.ric_entropy_decode_device.argtypes = [vp, vp, sz, vp, i, vp, vp, vp]
         L.ric_compress_u8_gpu.argtypes = [vp, vp, i, i, vp, sz, vp]
         L.ric_decompress_u8_gpu.argtypes = [vp, vp, sz, vp, i, vp]
         L.ric_mux_encoder.argtypes = [C.POINTER(vp), vp, sz, C.c_uint]
@@ -318,8 +318,9 @@ class Context:
     def entropy_encode_device(self, d_arenas, n, d_out, stride, d_sizes, stream=0):
         _check(self.L.ric_entropy_encode_device(self.h, _ptr(d_arenas), n, _ptr(d_out), stride, _ptr(d_sizes), stream))
 
-    def entropy_decode_device(self, d_payloads, stride, d_sizes, n, d_arenas, stream=0):
-        _check(self.L.ric_entropy_decode_device(self.h, _ptr(d_payloads), stride, _ptr(d_sizes), n, _ptr(d_arenas), stream))
+    def entropy_decode_device(self, d_payloads, stride, d_sizes, n, d_arenas, stream=0, d_status=None):
+        _check(self.L.ric_entropy_decode_device(self.h, _ptr(d_payloads), stride, _ptr(d_sizes), n, _ptr(d_arenas),
+                                                _ptr(d_status) if d_status is not None else None, stream))
 
     def set_profiling(self, on=True):
         _check(self.L.ric_set_profiling(self.h, int(on)))

@@ -1236,7 +1236,7 @@ int ric_entropy_encode_device(ric_ctx *c, void *d_arenas, int n, uint8_t *d_out,
 }
 
 int ric_entropy_decode_device(ric_ctx *c, const uint8_t *d_payloads, size_t stride, const long long *d_sizes, int n, void *d_arenas,
-                              void *stream)
+                              int *d_status, void *stream)
 {
 	if (!c || !d_arenas || !d_payloads || !d_sizes || n < 1) return set_err(RIC_E_ARG, "ric_entropy_decode_device: bad argument");
 	CK(cudaSetDevice(c->device));
@@ -1244,7 +1244,8 @@ int ric_entropy_decode_device(ric_ctx *c, const uint8_t *d_payloads, size_t stri
 	if (rc) return rc;
 	const size_t img_ar = (size_t)c->g.channels * c->g.arena_bytes;
 	CK(cudaMemsetAsync(d_arenas, 0, (size_t)n * img_ar, (cudaStream_t)stream));
-	CK(launch_entropy_decode(c->d_geom, c->d_tables, d_payloads, stride, d_sizes, (char *)d_arenas, img_ar, c->d_bad, n,
+	CK(cudaMemsetAsync(c->d_bad, 0, sizeof(int), (cudaStream_t)stream));  // (the context-wide flag of ric_decompress_u8_gpu)
+	CK(launch_entropy_decode(c->d_geom, c->d_tables, d_payloads, stride, d_sizes, (char *)d_arenas, img_ar, c->d_bad, d_status, n,
 	                         (cudaStream_t)stream));
 	return RIC_OK;
 }
@@ -1391,7 +1392,7 @@ int ric_decompress_u8_gpu(ric_ctx *c, const uint8_t *files, size_t stride, const
 		CK(cudaMemcpyAsync(c->d_psizes + i0, c->h_psizes + i0, sizeof(long long) * m, cudaMemcpyHostToDevice, es));
 		CK(cudaMemsetAsync(c->d_arena_in + i0 * img_ar, 0, (size_t)m * img_ar, es));
 		CK(launch_entropy_decode(c->d_geom, c->d_tables, c->d_payload + (size_t)i0 * c->payload_stride, c->payload_stride, c->d_psizes + i0,
-		                         c->d_arena_in + i0 * img_ar, img_ar, c->d_bad, m, es));
+		                         c->d_arena_in + i0 * img_ar, img_ar, c->d_bad, nullptr, m, es));
 		CK(cudaEventRecord(c->ent_ev[k], es));
 	}
 	k = 0;

@@ -31,18 +31,27 @@ __global__ void __launch_bounds__(64) entropy_encode_kernel(const HostGeom *gp, 
 
 // The arenas must have been cleared by the caller (CBand::Clear of every band, bandcodec.cpp:503).
 __global__ void __launch_bounds__(64) entropy_decode_kernel(const HostGeom *gp, const ent::Tables *T, const uint8_t *payloads, size_t stride,
-                                                            const long long *sizes, char *arenas, size_t img_ar, int *bad, int n)
+                                                            const long long *sizes, char *arenas, size_t img_ar, int *bad, int *status, int n)
 {
 	const int img = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
 	if (img >= n || (threadIdx.x & 31)) return;
 	const HostGeom &g = *gp;
+	if (status) status[img] = 0;
+	if (sizes[img] < 0 || (unsigned long long)sizes[img] > stride) {  // not a length this slot can hold: leave the (cleared) arenas alone
+		atomicExch(bad, 1);
+		if (status) status[img] = 1;
+		return;
+	}
 	ent::MuxReader r(payloads + (size_t)img * stride, (size_t)sizes[img]);
 	ent::RPort io(r, T);
 	for (int i = 0; i < g.channels; i++) {
 		const int plane = g.channels == 3 ? 2 - i : 0;
 		ent::walk_plane(io, g, arenas + (size_t)img * img_ar + (size_t)plane * g.arena_bytes);
 	}
-	if (r.overrun()) atomicExch(bad, 1);
+	if (r.overrun()) {
+		atomicExch(bad, 1);
+		if (status) status[img] = 1;
+	}
 }
 
 
@@ -106,9 +115,9 @@ cudaError_t launch_entropy_encode(const HostGeom *g, const void *tables, char *a
 }
 
 cudaError_t launch_entropy_decode(const HostGeom *g, const void *tables, const uint8_t *payloads, size_t stride, const long long *sizes,
-                                  char *arenas, size_t img_ar, int *bad, int n, cudaStream_t st)
+                                  char *arenas, size_t img_ar, int *bad, int *status, int n, cudaStream_t st)
 {
-	entropy_decode_kernel<<<(n + 1) / 2, 64, 0, st>>>(g, (const ent::Tables *)tables, payloads, stride, sizes, arenas, img_ar, bad, n);
+	entropy_decode_kernel<<<(n + 1) / 2, 64, 0, st>>>(g, (const ent::Tables *)tables, payloads, stride, sizes, arenas, img_ar, bad, status, n);
 	return cudaGetLastError();
 }
 

@@ -16,6 +16,6 @@ inline size_t hint_bytes(const HostGeom &hg, int n) { return (size_t)hg.flag_byt
 cudaError_t launch_entropy_encode_hinted(const HostGeom *g, const HostGeom &hg, const void *tables, char *arenas, size_t img_ar, void *hints,
                                          uint8_t *out, size_t stride, long long *sizes, int n, cudaStream_t st);
 cudaError_t launch_entropy_decode(const HostGeom *g, const void *tables, const uint8_t *payloads, size_t stride, const long long *sizes,
-                                  char *arenas, size_t img_ar, int *bad, int n, cudaStream_t st);
+                                  char *arenas, size_t img_ar, int *bad, int *status, int n, cudaStream_t st);
 
 }  // namespace ric

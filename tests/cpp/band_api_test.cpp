@@ -52,7 +52,7 @@ int main(int argc, char **argv)
 	const std::string out = argv[8];
 	try {
 		std::vector<char> plane = slurp(argv[6]);
-		CWavelet2D Wavelet(w, h, levels, levels - 4);
+		CWavelet2D Wavelet(w, h, levels, levels > 4 ? levels - 4 : 0);
 		Wavelet.SetWeight(cdf97);
 		Wavelet.Transform((short *)plane.data(), w, cdf97);
 		const std::vector<char> raw(Wavelet.arena(), Wavelet.arena() + Wavelet.arena_bytes());

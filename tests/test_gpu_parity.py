@@ -419,11 +419,11 @@ def test_bench_decode_input_preparation_matches_oracle_unfold():
 def test_ric_files_match_golden(golden):
     """Whole .ric files through ric_compress_u8 (GPU stage + product entropy stage on host threads): header
     bytes, payload size and CRC32 equal the reference's known answers; ric_decompress_u8
-    of those files gives the reference decoder's pixels."""
+    of those files gives the reference decoder's pixels.  Every known answer, the 8192 x 8192 gray image
+    (17 749 195 bytes, CRC 6ca7ca96) and the whole 4K quantiser sweep included."""
+    assert any(k["w"] == 8192 for k in golden["kats"]) and sum(k["w"] == 3840 for k in golden["kats"]) >= 8
     for k in golden["kats"]:
         w, h, ch, q = k["w"], k["h"], k["ch"], k["q"]
-        if w * h * ch > 3840 * 2160 * 3 or (w * h * ch > 1 << 22 and q not in (9, 27)):
-            continue
         img = synth_image(k["idx"], w, h, ch)
         with capi.Context(w, h, ch, k["levels"], trans=k["trans"]) as c:
             f = c.compress_u8(img[None], q)[0]
@@ -519,7 +519,9 @@ def test_entropy_stage_on_device(ch, q, trans, w, h):
                 o.unfold(arenas[p * o.arena_bytes:(p + 1) * o.arena_bytes])
             signed.append(arenas)
         back = torch.full((n * c.image_arena_bytes,), 0x5A, dtype=torch.uint8, device="cuda")
-        c.entropy_decode_device(out.data_ptr(), stride, sizes.data_ptr(), n, back.data_ptr(), st)
+        status = torch.full((n,), 7, dtype=torch.int32, device="cuda")
+        c.entropy_decode_device(out.data_ptr(), stride, sizes.data_ptr(), n, back.data_ptr(), st, d_status=status.data_ptr())
+        assert (status.cpu().numpy() == 0).all()
         dst = torch.zeros((n, ch, h, pitch), dtype=torch.uint8, device="cuda")
         c.decode_u8_device(back.data_ptr(), n, q, dst.data_ptr(), pitch, st)
         torch.cuda.synchronize()
@@ -532,6 +534,20 @@ def test_entropy_stage_on_device(ch, q, trans, w, h):
         c.entropy_encode_device(ar.data_ptr(), n, small.data_ptr(), 64, sizes.data_ptr(), st)
         torch.cuda.synchronize()
         assert (sizes.cpu().numpy() == -1).all()
+        # ... and the decoder reports bad inputs per image: a negative length, a truncated payload, a
+        # payload of 0xFF bytes (no code of the format has that shape); the good images still decode
+        if n >= 3:
+            bad_sizes = torch.from_numpy(sizes_h.copy()).cuda()
+            bad_sizes[0] = -1
+            bad_sizes[1] = max(int(sizes_h[1]) // 3, 1)
+            junk = out.clone()
+            junk.view(n, stride)[2, :] = 0xFF
+            c.entropy_decode_device(junk.data_ptr(), stride, bad_sizes.data_ptr(), n, back.data_ptr(), st, d_status=status.data_ptr())
+            torch.cuda.synchronize()
+            stat = status.cpu().numpy()
+            assert stat[0] == 1 and stat[1] == 1 and stat[2] == 1 and (stat[3:] == 0).all(), stat
+            per = c.image_arena_bytes
+            assert np.array_equal(back[3 * per:].cpu().numpy(), np.concatenate(signed[3:])) if n > 3 else True
 
 
 def test_ric_file_many_workers():
