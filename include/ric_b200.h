@@ -108,7 +108,12 @@ int ric_sync(ric_ctx *ctx);
 
 /* ---- device-resident variants (no copies; asynchronous on `stream`, a cudaStream_t) ------------
  * d_src pitch: bytes between rows (multiple of 8); planes are pitch*height apart, images
- * channels*pitch*height apart.  d_arenas as above but in device memory.  d_dst likewise. */
+ * channels*pitch*height apart.  d_arenas as above but in device memory.  d_dst likewise.
+ * CONCURRENCY: a context is ONE CWavelet2D-like object -- its LL scratch planes, block flags and job counters are
+ * shared by every call.  Keep at most one call per context in flight: issue the *_device calls of a context on
+ * one stream (or order them yourself with events), and let a *_stream / ric_compress / plane-level call return
+ * (ric_sync for the *_stream pair) before the next call on the same context.  Independent work goes on separate
+ * contexts, which share nothing (bench.py runs the encode and the decode stage concurrently on two). */
 int ric_encode_u8_device(ric_ctx *ctx, const uint8_t *d_src, size_t pitch, int n, int q,
                          void *d_arenas, void *stream);
 int ric_decode_u8_device(ric_ctx *ctx, const void *d_arenas, int n, int q, uint8_t *d_dst,

@@ -340,9 +340,15 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	c->g = g;
 	c->device = device;
 	c->max_batch = max_batch;
-	cudaDeviceProp prop;
-	CK(cudaGetDeviceProperties(&prop, device));
-	c->sm_count = prop.multiProcessorCount;
+	{
+		int sms = 0;
+		cudaError_t pe = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+		if (pe != cudaSuccess) {
+			delete c;
+			return set_err(RIC_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(pe));
+		}
+		c->sm_count = sms;
+	}
 	const char *tw = getenv("RIC_TARGET_WARPS");
 	c->target_warps = tw ? atoi(tw) : 0;  // override of the concurrent-job count used by choose_seg_rows
 	// ric_fwd0.cuh: measured 6 % slower than the scalar kernel with the packed quantiser (12 warps per SM against
@@ -1297,7 +1303,9 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 	CK(cudaSetDevice(c->device));
 	const size_t img_px = (size_t)g.channels * g.height * g.width, img_dev = (size_t)g.channels * g.height * c->src_pitch;
 	const size_t img_ar = (size_t)g.channels * g.arena_bytes;
-	const size_t pstride = std::min(stride - RIC_HEADER_BYTES, (img_px + 15) & ~(size_t)15) & ~(size_t)15;  // the reference's own bound is W*H*C
+	// device payload slots follow the caller's stride (like the host path), up to 2 x W*H*C + 4096 -- twice the
+	// reference's own buffer (W*H*C, ric.cpp:131-132; incompressible input at q = 0 can exceed it)
+	const size_t pstride = std::min(stride - RIC_HEADER_BYTES, 2 * img_px + 4096) & ~(size_t)15;
 	if ((rc = need_payload(c, pstride))) return rc;
 	if ((rc = sync_pipe(c))) return rc;
 	// Pixel copies + encode stage chunk by chunk on the pipeline streams, then ONE entropy launch over the whole
@@ -1344,12 +1352,16 @@ int ric_compress_u8_gpu(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *f
 		ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
 		if (c->h_psizes[i] < 0) { small = true; sizes[i] = 0; continue; }
 		sizes[i] = (size_t)c->h_psizes[i] + RIC_HEADER_BYTES;
-		CK(cudaMemcpyAsync(f + RIC_HEADER_BYTES, c->d_payload + (size_t)i * c->payload_stride, (size_t)c->h_psizes[i],
-		                   cudaMemcpyDeviceToHost, c->pipe[i % 3]));
+		cudaError_t ce = cudaMemcpyAsync(f + RIC_HEADER_BYTES, c->d_payload + (size_t)i * c->payload_stride, (size_t)c->h_psizes[i],
+		                                 cudaMemcpyDeviceToHost, c->pipe[i % 3]);
+		if (ce != cudaSuccess) {  // copies into the caller's buffer are in flight: drain them before returning
+			sync_pipe(c);
+			return set_err(RIC_E_CUDA, "ric_compress_u8_gpu: %s", cudaGetErrorString(ce));
+		}
 	}
 	if ((rc = sync_pipe(c))) return rc;
 	stamp("files fetched", n);
-	if (small) return set_err(RIC_E_NOMEM, "ric_compress_u8_gpu: a file did not fit in `stride` bytes");
+	if (small) return set_err(RIC_E_NOMEM, "ric_compress_u8_gpu: a file did not fit in its slot (min(stride, 2*W*H*C + 4096) bytes)");
 	return RIC_OK;
 }
 

@@ -1,0 +1,28 @@
+"""Development probe: level times of the decode stage."""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np, torch
+from rududu_image_codec_b200 import capi
+from rududu_image_codec_b200.synth import synth_image
+
+def run(w, h, ch, levels, n, q=9):
+    imgs = np.stack([synth_image(i, w, h, ch) for i in range(min(n, 4))])
+    c = capi.Context(w, h, ch, levels, max_batch=n)
+    pitch = (w + 15) & ~7
+    src = torch.zeros((n, ch, h, pitch), dtype=torch.uint8, device="cuda")
+    src[:, :, :, :w] = torch.from_numpy(imgs).cuda().repeat((n + 3) // 4, 1, 1, 1)[:n]
+    ar = torch.zeros(n * c.image_arena_bytes + 64, dtype=torch.uint8, device="cuda")
+    dst = torch.zeros_like(src)
+    st = torch.cuda.current_stream().cuda_stream
+    c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
+    c.set_profiling(True)
+    for _ in range(4):
+        c.decode_u8_device(ar.data_ptr(), n, q, dst.data_ptr(), pitch, st)
+    torch.cuda.synchronize()
+    print("%dx%dx%d n=%d q=%d decode level ms %s" % (w, h, ch, n, q, ["%.3f" % t for t in c.level_times(1)]), flush=True)
+    c.close()
+
+if __name__ == "__main__":
+    run(3840, 2160, 3, 5, 32)
+    run(1920, 1080, 3, 5, 64)
+    run(8192, 8192, 1, 6, 2)
