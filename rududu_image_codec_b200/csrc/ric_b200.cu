@@ -85,6 +85,7 @@ struct ric_ctx {
 	cudaEvent_t ev[2][RIC_MAX_LEVELS + 1];  // [direction][launch boundary]
 	int ev_n[2];
 	int target_warps;
+	int use_tma;
 	int use_fwd0;                        // packed level-0 forward kernel, experimental (RIC_FWD0=1)
 };
 
@@ -233,6 +234,27 @@ static void fill_qb(QuantBand &q, int Quant, int lambda, float weight, int is_in
 	q.h0 = std::max(hq.thr[0] >> 1, hq.T + 1);
 }
 
+// 2-D tensor map over a u8 source for the TMA experiment of ric_fwd0.cuh (width x rows, row pitch in bytes).
+// The encoder lives in the driver; it is fetched through the runtime so that the library needs no libcuda link.
+static bool make_src_tensor_map(CUtensorMap *map, const void *base, int width, unsigned long long rows, int pitch, unsigned box_w)
+{
+	typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+	                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+	                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+	static encode_fn fn = nullptr;
+	if (!fn) {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+		fn = (encode_fn)p;
+	}
+	if ((pitch & 15) || ((uintptr_t)base & 15)) return false;  // the unit wants 16-byte aligned rows
+	const cuuint64_t dim[2] = {(cuuint64_t)width, rows}, stride[1] = {(cuuint64_t)pitch};
+	const cuuint32_t box[2] = {box_w, 2}, es[2] = {1, 1};
+	return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static BandRef band_ref(const HostGeom &g, int id)
 {
 	BandRef r;
@@ -354,6 +376,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	// ric_fwd0.cuh: measured 6 % slower than the scalar kernel with the packed quantiser (12 warps per SM against
 	// 16: profiles/README.md), so it is opt-in
 	c->use_fwd0 = getenv("RIC_FWD0", 0);
+	c->use_tma = getenv("RIC_TMA", 0);  // gray level 0 of the packed kernel through the TMA unit (experiment, profiles/README.md)
 #define CKD(call)                                                                    \
 	do {                                                                             \
 		cudaError_t e_ = (call);                                                     \
@@ -366,6 +389,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CKD(cudaFuncSetAttribute(fwd0_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f0_smem_bytes<3>()));
 	CKD(cudaFuncSetAttribute(fwd0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f0_smem_bytes<1>()));
+	CKD(cudaFuncSetAttribute(fwd0_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f0_smem_bytes_tma()));
 	for (int i = 0; i < 3; i++) CKD(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
 	const size_t nb = (size_t)max_batch, ch = (size_t)channels;
 	c->src_pitch = ((size_t)width + 7) & ~(size_t)7;  // roundup8(w): dense rows (one contiguous copy) when w % 8 == 0
@@ -564,7 +588,11 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 			const long long njobs = (long long)P.nstrips * P.nsegs * n;
 			if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "forward: batch too large for one launch");
 			const unsigned grid = (unsigned)std::min<long long>((njobs + F0_WARPS - 1) / F0_WARPS, (long long)c->sm_count * occ);
+			CUtensorMap tmap, tmapB;
 			if (nplanes == 3) fwd0_kernel<3><<<grid, F0_WARPS * 32, f0_smem_bytes<3>(), st>>>(P);
+			else if (c->use_tma && make_src_tensor_map(&tmap, d_src, P.w, (unsigned long long)n * P.h, src_pitch, 256) &&
+			         make_src_tensor_map(&tmapB, d_src, P.w, (unsigned long long)n * P.h, src_pitch, 16))
+				fwd0_tma_kernel<<<grid, F0_WARPS * 32, f0_smem_bytes_tma(), st>>>(P, tmap, tmapB);
 			else fwd0_kernel<1><<<grid, F0_WARPS * 32, f0_smem_bytes<1>(), st>>>(P);
 		} else {
 			fwd_fn fn = pick_fwd(sh, g.trans, src);

@@ -22,6 +22,8 @@
 // Host side (ric_b200.cu launch_forward) uses this kernel when: 9/7, short level 0, more than one level,
 // q != 0 (up-shifted pixels; q == 0 keeps the scalar kernel).
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only: the encoder is fetched through the runtime, no libcuda link)
+
 #include "ric_fwd.cuh"
 #include "ric_swar.cuh"
 
@@ -41,9 +43,53 @@ struct F0Smem {  // lane-private staging of one warp
 	uint4 state[NP][4][32];  // column-pass pipeline: raw odd row, S1'd even row, S2'd odd row, S3'd even row
 };
 
+// ---- TMA experiment (gray level 0): one bulk tensor copy per warp and row pair instead of 64 per-lane loads ----
+// Two 2-D tensor maps over the u8 source (width W, all image rows back to back, row pitch `pitch`), boxes of
+// 256 x 2 and 16 x 2 bytes: the unit wants the box to start on a 16-byte boundary (a start at x0 - 8 traps with
+// "illegal instruction", scripts/ubench/tma_probe.cu), so a strip's columns x0-8 .. x0+247 of rows 2t, 2t+1 come
+// as the box at x0-16 plus a 16-byte box at x0+240.  Columns left of 0 / right of W-1 are zero-filled by the unit
+// (what the `col_ok ? load : 0` predicates did).  Lane 0 arms an mbarrier with the byte count and issues the
+// copies; every lane waits on the barrier and reads its 8 bytes per row from shared memory.
+struct F0Tma {
+	alignas(128) unsigned char tile[2][640];  // double-buffered: [stage]: rows of box A [2][256], rows of box B [2][16], pad
+	unsigned long long bar[2];
+};
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f0_mbar_init(unsigned long long *bar)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void f0_tma_issue(const CUtensorMap *mapA, const CUtensorMap *mapB, unsigned char *dst, unsigned long long *bar,
+                                             int x0, int y)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 544;" ::"r"(smem_u32(bar)) : "memory");
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             ::"r"(smem_u32(dst)), "l"(mapA), "r"(x0 - 16), "r"(y), "r"(smem_u32(bar))
+	             : "memory");
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+	             ::"r"(smem_u32(dst + 512)), "l"(mapB), "r"(x0 + 240), "r"(y), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void f0_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "RIC_F0_WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra RIC_F0_DONE_%=;\n"
+	    "bra RIC_F0_WAIT_%=;\n"
+	    "RIC_F0_DONE_%=:\n"
+	    "}\n" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+
 __host__ __device__ constexpr size_t f0_qb_bytes() { return (sizeof(QuantBand) * 6 + 15) & ~(size_t)15; }
 template <int NP>
 __host__ __device__ constexpr size_t f0_smem_bytes() { return f0_qb_bytes() + F0_WARPS * sizeof(F0Smem<NP>); }
+__host__ __device__ constexpr size_t f0_tma_off() { return (f0_smem_bytes<1>() + 127) & ~(size_t)127; }
+__host__ __device__ constexpr size_t f0_smem_bytes_tma() { return f0_tma_off() + F0_WARPS * sizeof(F0Tma); }
 
 // ---- pixels -> row-pass input ---------------------------------------------------------------------------
 // X[c] = (row 2t | row 2t+1 << 16) of column c, constants KH::E0 (even c) / KH::O0 (odd c).
@@ -194,9 +240,10 @@ __device__ __noinline__ void f0_row_pass_edge(unsigned (&X)[8], int cb, int w, i
 }
 
 // One job = one (image, row segment, strip), all NP planes.
-template <int NP>
+template <int NP, bool TMA>
 __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, int sx, bool EDGE, F0Smem<NP> &sm,
-                                         const QuantBand (*s_qb)[3], int lane)
+                                         const QuantBand (*s_qb)[3], int lane, const CUtensorMap *tmap, const CUtensorMap *tmapB, F0Tma *tm,
+                                         unsigned &tma_par)
 {
 	using namespace sw;
 	const int w = P.w, h = P.h;
@@ -226,6 +273,11 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 	const int t_begin = (y0 >> 1) - 2, t_last = (y1r >> 1) + 1;
 	uint2 rawE[NP], rawO[NP];
 	auto load_rows = [&](int t) {
+		if constexpr (TMA) {  // (NP == 1) issue the bulk copy of rows 2t, 2t+1 into stage (t & 1); read back by take_rows
+			__syncwarp();     // every lane is done with the stage this copy overwrites
+			if (lane == 0) f0_tma_issue(tmap, tmapB, tm->tile[t & 1], &tm->bar[t & 1], x0, img * h + 2 * t);
+			return;
+		}
 		const int re = 2 * t, ro = re + 1;
 		const bool oke = col_ok && re >= 0 && re < h, oko = col_ok && ro >= 0 && ro < h;
 #pragma unroll
@@ -235,10 +287,22 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 			if (oko) rawO[p] = __ldg((const uint2 *)(src + p * P.src_plane_stride + (long long)ro * P.src_pitch));
 		}
 	};
+	auto take_rows = [&](int t) {
+		if constexpr (TMA) {
+			const int st = t & 1;
+			f0_mbar_wait(&tm->bar[st], (tma_par >> st) & 1u);
+			tma_par ^= 1u << st;
+			// box A holds columns x0-16 .. x0+239, this lane's start at x0-8+8*lane; lane 31's eight are box B's first
+			const unsigned char *rowE = lane < 31 ? tm->tile[st] + 8 + lane * 8 : tm->tile[st] + 512;
+			rawE[0] = *(const uint2 *)rowE;
+			rawO[0] = *(const uint2 *)(rowE + (lane < 31 ? 256 : 16));
+		}
+	};
 	load_rows(t_begin);
 
 #pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
+		take_rows(t);
 		{  // pixels -> row-pass input of every plane, staged in shared memory for the rolled plane loop
 			if constexpr (NP == 3) {
 				unsigned Xp[3][8];
@@ -347,17 +411,25 @@ __device__ __forceinline__ void fwd0_job(const FwdParams &P, int img, int sy, in
 			}
 		}
 	}
+	take_rows(t_last + 1);  // (TMA) the last prefetch is still in flight: its stage must be free before the next job
 }
 
-template <int NP>
-__global__ void __launch_bounds__(F0_WARPS * 32, NP == 3 ? 3 : 4) fwd0_kernel(const __grid_constant__ FwdParams P)
+template <int NP, bool TMA>
+__device__ __forceinline__ void fwd0_body(const FwdParams &P, const CUtensorMap *tmap, const CUtensorMap *tmapB)
 {
-	extern __shared__ __align__(16) unsigned char f0_smem[];
+	extern __shared__ __align__(128) unsigned char f0_smem[];
 	QuantBand(*s_qb)[3] = (QuantBand(*)[3])f0_smem;
 	for (int i = threadIdx.x; i < (int)(sizeof(QuantBand) * 6 / 4); i += blockDim.x) ((int *)f0_smem)[i] = ((const int *)P.qb)[i];
-	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	F0Smem<NP> &sm = *((F0Smem<NP> *)(f0_smem + f0_qb_bytes()) + wib);
+	F0Tma *tm = TMA ? (F0Tma *)(f0_smem + f0_tma_off()) + wib : nullptr;
+	unsigned tma_par = 0;
+	if (TMA && lane == 0) {
+		f0_mbar_init(&tm->bar[0]);
+		f0_mbar_init(&tm->bar[1]);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
 	const unsigned njobs = (unsigned)P.nstrips * P.nsegs * P.nimages;
 	for (;;) {
 		unsigned long long j64 = 0;
@@ -369,8 +441,21 @@ __global__ void __launch_bounds__(F0_WARPS * 32, NP == 3 ? 3 : 4) fwd0_kernel(co
 		const int sy = (int)(job % (unsigned)P.nsegs);
 		const int img = (int)(job / (unsigned)P.nsegs);
 		const int x0 = sx * STRIP_W;
-		fwd0_job<NP>(P, img, sy, sx, (x0 == 0) || (P.w <= x0 + STRIP_W + LANE_W), sm, s_qb, lane);
+		fwd0_job<NP, TMA>(P, img, sy, sx, (x0 == 0) || (P.w <= x0 + STRIP_W + LANE_W), sm, s_qb, lane, tmap, tmapB, tm, tma_par);
 	}
+}
+
+template <int NP>
+__global__ void __launch_bounds__(F0_WARPS * 32, NP == 3 ? 3 : 4) fwd0_kernel(const __grid_constant__ FwdParams P)
+{
+	fwd0_body<NP, false>(P, nullptr, nullptr);
+}
+
+// gray only: the source rows come through the TMA unit (RIC_TMA=1, with RIC_FWD0=1)
+__global__ void __launch_bounds__(F0_WARPS * 32, 4) fwd0_tma_kernel(const __grid_constant__ FwdParams P, const __grid_constant__ CUtensorMap tmap,
+                                                                    const __grid_constant__ CUtensorMap tmapB)
+{
+	fwd0_body<1, true>(P, &tmap, &tmapB);
 }
 
 }  // namespace ric

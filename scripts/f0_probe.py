@@ -8,7 +8,7 @@ from rududu_image_codec_b200.synth import synth_image
 def run(w, h, ch, levels, n, q=9):
     imgs = np.stack([synth_image(i, w, h, ch) for i in range(min(n, 4))])
     c = capi.Context(w, h, ch, levels, max_batch=n)
-    pitch = (w + 15) & ~7
+    pitch = (w + 15) & ~15
     src = torch.zeros((n, ch, h, pitch), dtype=torch.uint8, device="cuda")
     src[:, :, :, :w] = torch.from_numpy(imgs).cuda().repeat((n + 3) // 4, 1, 1, 1)[:n]
     ar = torch.zeros(n * c.image_arena_bytes + 64, dtype=torch.uint8, device="cuda")
