@@ -130,7 +130,8 @@ int ric_get_level_times(ric_ctx *ctx, int direction, float *ms, int cap);
 /* Path statistics of the packed (two samples per register) kernels, counted while profiling is on and reset
  * by this call: out[0] = plane iterations (one row pair of one plane of one strip) run by the packed forward
  * kernel, out[1] = how many of them took the scalar, exactly-wrapping path (image edge rows, or operands outside
- * the bounds the packed arithmetic needs); out[2], out[3] the same for the packed inverse kernel.  n <= 8. */
+ * the bounds the packed arithmetic needs); out[2] = plane iterations of the packed inverse kernel, out[3] / out[4] = how
+ * many of their column / row passes took the scalar path.  n <= 8. */
 int ric_get_path_stats(ric_ctx *ctx, unsigned long long *out, int n);
 
 /* ---- plane-level entry points mirroring the reference class API (HOST buffers) -------------------

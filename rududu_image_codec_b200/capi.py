@@ -326,9 +326,9 @@ class Context:
         _check(self.L.ric_set_profiling(self.h, int(on)))
 
     def path_stats(self):
-        """Packed-kernel path counters since the last call (profiling must be on): [fwd iterations, fwd scalar, inv iterations, inv scalar]."""
-        buf = (C.c_ulonglong * 4)()
-        _check(self.L.ric_get_path_stats(self.h, buf, 4))
+        """Packed-kernel path counters since the last call (profiling must be on): [fwd iterations, fwd scalar, inv iterations, inv scalar column passes, inv scalar row passes]."""
+        buf = (C.c_ulonglong * 5)()
+        _check(self.L.ric_get_path_stats(self.h, buf, 5))
         return [int(v) for v in buf]
 
     def level_times(self, direction):

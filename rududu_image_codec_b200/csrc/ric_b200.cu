@@ -22,6 +22,7 @@
 #include "ric_fwd0.cuh"
 #include "ric_host.h"
 #include "ric_inv.cuh"
+#include "ric_inv0.cuh"
 
 using namespace ric;
 
@@ -86,6 +87,7 @@ struct ric_ctx {
 	int ev_n[2];
 	int target_warps;
 	int use_tma;
+	int use_inv0;
 	int use_fwd0;                        // packed level-0 forward kernel, experimental (RIC_FWD0=1)
 };
 
@@ -376,6 +378,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	// ric_fwd0.cuh: measured 6 % slower than the scalar kernel with the packed quantiser (12 warps per SM against
 	// 16: profiles/README.md), so it is opt-in
 	c->use_fwd0 = getenv("RIC_FWD0", 0);
+	c->use_inv0 = getenv("RIC_INV0", 0);  // packed finest inverse level (ric_inv0.cuh)
 	c->use_tma = getenv("RIC_TMA", 0);  // gray level 0 of the packed kernel through the TMA unit (experiment, profiles/README.md)
 #define CKD(call)                                                                    \
 	do {                                                                             \
@@ -668,7 +671,19 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 		const long long njobs = (long long)P.nstrips * P.nsegs * jplanes * n;
 		if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "inverse: batch too large for one launch");
 		P.counter = ctr + lv;
-		if (dst == DST_U8_RGB) {
+		P.stats = c->profiling ? c->d_stats : nullptr;
+		// finest level to 8-bit pixels: the packed kernel (ric_inv0.cuh)
+		const bool packed0 = c->use_inv0 && lv == 0 && sh && shift && g.trans == RIC_CDF97 && P.llsrc == LLSRC_S16 &&
+		                     ((dst == DST_U8_RGB && nplanes == 3) || (dst == DST_U8_GRAY && nplanes == 1));
+		if (packed0) {
+			if (dst == DST_U8_RGB) {
+				const unsigned grid = (unsigned)std::min<long long>(njobs, (long long)c->sm_count * 6);
+				inv0_kernel<DST_U8_RGB><<<grid, 96, 0, st>>>(P);
+			} else {
+				const unsigned grid = (unsigned)std::min<long long>((njobs + INV_WARPS - 1) / INV_WARPS, (long long)c->sm_count * 4);
+				inv0_kernel<DST_U8_GRAY><<<grid, INV_WARPS * 32, 0, st>>>(P);
+			}
+		} else if (dst == DST_U8_RGB) {
 			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * (6 / INV_RGB_GROUPS));
 			fn<<<grid, INV_RGB_GROUPS * 96, 0, st>>>(P);
 		} else {

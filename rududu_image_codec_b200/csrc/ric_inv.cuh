@@ -43,6 +43,7 @@ struct InvParams {
 	int shift;                 // q != 0: undo the fixed-point up-shift and clip (ric.cpp:98-110,237-240)
 	int dq[3][4];              // TSUQi multiplier per plane for D,H,V,L (1 = no dequantisation)
 	unsigned long long *counter;  // dynamic job fetch (zeroed before the launch)
+	unsigned long long *stats;    // optional (profiling): [2] packed-kernel plane iterations, [3] scalar column passes, [4] scalar row passes
 };
 
 __device__ __forceinline__ int clip255(int v) { return __vimin_s32_relu(v, 255); }  // max(min(v, 255), 0), one VIMNMX.RELU

@@ -154,5 +154,98 @@ constexpr unsigned GUARD_E = 0xC000C000u;  // (R & GUARD_E) == 0  <=>  both S1'd
 // bounds that then hold for the derived rows (ric_fwd0.cuh, v_slow re-checks them on the scalar path):
 constexpr int BOUND_O0 = 4095, BOUND_E1 = 8191, BOUND_O2 = 5119, BOUND_E3 = 16381;
 
+
+// ---- inverse 9/7 steps (src/lib/wavelet2d.cpp:361-405) ---------------------------------
+// Here every register, at every stage, carries the SAME constant G = 0x2000 per half: a value is inside the
+// range the packed path may use, [-8192, 8191], exactly when (R & GUARD_I) == 0, so one OR over everything an
+// iteration produced tests all of it at once.  With every stored value in that range no intermediate of the next
+// step can leave int16 (sums <= 16382, t + (t >> 1) <= 24573, x + that <= 32764), which is what makes the linear
+// arithmetic equal to the reference's wrapping `short` arithmetic.  The constants that restore G ride on the
+// three-input adds.
+constexpr unsigned G = 0x20002000u;
+constexpr unsigned GUARD_I = 0xC000C000u;
+constexpr unsigned CSUM = OB - 2u * G;  // neighbour sum l + r + CSUM has constant OB
+RIC_HD unsigned u4(unsigned x, unsigned l, unsigned r)  // x -= (t >> 1) - (t >> 5), t = l + r
+{
+	const unsigned b = l + r + CSUM;
+	return x + ((OB >> 1) - (OB >> 5)) + lsr<5>(b) - lsr<1>(b);
+}
+RIC_HD unsigned u3(unsigned x, unsigned l, unsigned r)  // x -= mult08(l + r)
+{
+	unsigned a = l + r + CSUM;
+	a -= lsr<2>(a);
+	a += lsr<4>(a);  // constant 0x6600 per half, then + (0x6600 >> 8)
+	return x + 0x66666666u - a - lsr<8>(a);
+}
+RIC_HD unsigned u2(unsigned x, unsigned l, unsigned r) { return x - (OB >> 4) + lsr<4>(l + r + CSUM); }  // x += (l + r) >> 4
+RIC_HD unsigned u1(unsigned x, unsigned l, unsigned r)  // x += t + (t >> 1)
+{
+	const unsigned b = l + r + CSUM;
+	return x - (OB + (OB >> 1)) + b + lsr<1>(b);
+}
+// edge formulas of the row pass: one neighbour n (wavelet2d.cpp:365-368,388-403)
+RIC_HD unsigned u4_last(unsigned x, unsigned l)  // x -= l - (l >> 4)
+{
+	const unsigned b = l + (OB - G);
+	return x + (OB - (OB >> 4)) - b + lsr<4>(b);
+}
+RIC_HD unsigned u3_edge(unsigned x, unsigned n)  // x -= 2 * mult08(n)
+{
+	unsigned a = n + (OB - G);
+	a -= lsr<2>(a);
+	a += lsr<4>(a);
+	const unsigned m = a + lsr<8>(a);  // constant 0x6666 per half
+	return x + 2u * 0x66666666u - 2u * m;
+}
+RIC_HD unsigned u2_last(unsigned x, unsigned l) { return x - (OB >> 3) + lsr<3>(l + (OB - G)); }  // x += l >> 3
+RIC_HD unsigned u1_edge(unsigned x, unsigned n) { return x - 3u * G + 3u * n; }                    // x += 3 n
+
+// TSUQi (src/lib/band.h:94-107) on a pair of two's-complement coefficients: c * q per half, constant G.
+// Only valid while |c * q| <= 8191 in both halves (the caller bounds |c| first): kfix = G - OB * q.
+RIC_HD unsigned dequant(unsigned c2, unsigned q, unsigned kfix) { return (c2 ^ OB) * q + kfix; }
+
+// Pixel outputs are clamped as value + PIXK per half: both halves non-negative (so the register is readable half by
+// half) and the low byte of each half is the pixel.
+RIC_HD unsigned vmaxs2(unsigned a, unsigned b)
+{
+#ifdef __CUDA_ARCH__
+	return __vmaxs2(a, b);
+#else
+	const int al = (short)(a & 0xFFFF), ah = (short)(a >> 16), bl = (short)(b & 0xFFFF), bh = (short)(b >> 16);
+	return (unsigned)((al > bl ? al : bl) & 0xFFFF) | (unsigned)((ah > bh ? ah : bh) & 0xFFFF) << 16;
+#endif
+}
+RIC_HD unsigned vmins2(unsigned a, unsigned b)
+{
+#ifdef __CUDA_ARCH__
+	return __vmins2(a, b);
+#else
+	const int al = (short)(a & 0xFFFF), ah = (short)(a >> 16), bl = (short)(b & 0xFFFF), bh = (short)(b >> 16);
+	return (unsigned)((al < bl ? al : bl) & 0xFFFF) | (unsigned)((ah < bh ? ah : bh) & 0xFFFF) << 16;
+#endif
+}
+constexpr unsigned PIXK = 0x41004100u;
+RIC_HD unsigned clip_pix(unsigned v) { return vmins2(vmaxs2(v, PIXK), PIXK + 0x00FF00FFu); }  // clamp(value, 0, 255) + PIXK
+// inverse level shift of a gray pair: clip(128 + ((v + 8) >> 4)), ric.cpp:237-240
+RIC_HD unsigned gray_out(unsigned v)  // v: constant G
+{
+	const unsigned s = lsr<4>(v + (OB - G) + 0x00080008u);     // ((v + 8) >> 4) + 0x0800
+	return clip_pix(s + (PIXK + 0x00800080u - (OB >> 4)));     // + 128
+}
+// YCoCgtoRGB<4> (ric.cpp:93-112) on pairs, constant G in, clamped value + PIXK out (r, g, b by reference)
+RIC_HD void ycocg_out(unsigned co, unsigned cg, unsigned y, unsigned &r, unsigned &g, unsigned &b)
+{
+	const unsigned co3 = lsr<3>(co + (OB - G) + 0x00040004u);  // ((co + 4) >> 3) + 0x1000
+	const unsigned cg3 = lsr<3>(cg + (OB - G) + 0x00040004u);  // ((cg + 4) >> 3) + 0x1000
+	const unsigned y4 = lsr<4>(y + (OB - G) + 0x00080008u);    // ((y + 8) >> 4) + 0x0800
+	const unsigned yb = y4 + 0x00800080u - lsr<1>(cg3);        // y -= (cg >> 1) - 128      constant 0: may be "negative"
+	const unsigned gg = cg3 + yb;                              // cg += y                  constant 0x1000
+	const unsigned bb = yb - lsr<1>(co3);                      // y -= co >> 1             constant -0x0800
+	const unsigned rr = co3 + bb;                              // co += y                  constant 0x0800
+	r = clip_pix(rr + (PIXK - 0x08000800u));
+	g = clip_pix(gg + (PIXK - 0x10001000u));
+	b = clip_pix(bb + (PIXK + 0x08000800u));
+}
+
 }  // namespace sw
 }  // namespace ric

@@ -15,11 +15,23 @@ def run(w, h, ch, levels, n, q=9):
     dst = torch.zeros_like(src)
     st = torch.cuda.current_stream().cuda_stream
     c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
+    torch.cuda.synchronize()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    bench.unfold_arenas_(c, ar, min(n, 4))  # signed coefficients, as the entropy decoder leaves them
+    per = c.image_arena_bytes
+    for i in range(4, n):
+        ar[i * per:(i + 1) * per].copy_(ar[(i % 4) * per:((i % 4) + 1) * per])
     c.set_profiling(True)
     for _ in range(4):
         c.decode_u8_device(ar.data_ptr(), n, q, dst.data_ptr(), pitch, st)
     torch.cuda.synchronize()
-    print("%dx%dx%d n=%d q=%d decode level ms %s" % (w, h, ch, n, q, ["%.3f" % t for t in c.level_times(1)]), flush=True)
+    lt = c.level_times(1)
+    c.path_stats()
+    c.decode_u8_device(ar.data_ptr(), n, q, dst.data_ptr(), pitch, st)
+    torch.cuda.synchronize()
+    print("%dx%dx%d n=%d q=%d INV0=%s decode level ms %s stats %s" % (w, h, ch, n, q, os.environ.get("RIC_INV0", "0"), ["%.3f" % t for t in lt], c.path_stats()), flush=True)
     c.close()
 
 if __name__ == "__main__":

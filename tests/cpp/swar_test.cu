@@ -175,8 +175,122 @@ static void test_guard()
 	}
 }
 
+// ---- inverse ----------------------------------------------------------------------------------------------
+// reference: the step-parallel form of TransLine97I, C = short
+static void ref_line_inv(std::vector<short> &x)
+{
+	const int n = (int)x.size();
+	for (int i = 1; i < n; i += 2) {  // U4
+		if (i == n - 1) x[i] -= x[i - 1] - (x[i - 1] >> 4);
+		else { short t = x[i - 1] + x[i + 1]; x[i] -= (t >> 1) - (t >> 5); }
+	}
+	for (int i = 0; i < n; i += 2) {  // U3
+		if (i == 0) x[i] -= 2 * m08s(x[1]);
+		else if (i == n - 1) x[i] -= 2 * m08s(x[i - 1]);
+		else x[i] -= m08i(x[i - 1] + x[i + 1]);
+	}
+	for (int i = 1; i < n; i += 2) {  // U2
+		if (i == n - 1) x[i] += x[i - 1] >> 3;
+		else x[i] += (x[i - 1] + x[i + 1]) >> 4;
+	}
+	for (int i = 0; i < n; i += 2) {  // U1
+		if (i == 0) x[i] += 3 * x[1];
+		else if (i == n - 1) x[i] += 3 * x[i - 1];
+		else { short t = x[i - 1] + x[i + 1]; x[i] += t + (t >> 1); }
+	}
+}
+
+// packed inverse of two lines at once; returns false when any produced value fails the guard
+static bool packed_line_inv(std::vector<unsigned> &X)
+{
+	const int n = (int)X.size();
+	unsigned acc = 0;
+	for (int i = 0; i < n; i++) acc |= X[i];
+	std::vector<unsigned> o(X);
+	for (int i = 1; i < n; i += 2) { X[i] = i == n - 1 ? u4_last(o[i], o[i - 1]) : u4(o[i], o[i - 1], o[i + 1]); acc |= X[i]; }
+	o = X;
+	for (int i = 0; i < n; i += 2) { X[i] = i == 0 ? u3_edge(o[i], o[1]) : i == n - 1 ? u3_edge(o[i], o[i - 1]) : u3(o[i], o[i - 1], o[i + 1]); acc |= X[i]; }
+	o = X;
+	for (int i = 1; i < n; i += 2) { X[i] = i == n - 1 ? u2_last(o[i], o[i - 1]) : u2(o[i], o[i - 1], o[i + 1]); acc |= X[i]; }
+	o = X;
+	for (int i = 0; i < n; i += 2) { X[i] = i == 0 ? u1_edge(o[i], o[1]) : i == n - 1 ? u1_edge(o[i], o[i - 1]) : u1(o[i], o[i - 1], o[i + 1]); acc |= X[i]; }
+	return (acc & GUARD_I) == 0;
+}
+
+static void test_inverse()
+{
+	int used = 0, rejected = 0;
+	for (int iter = 0; iter < 30000; iter++) {
+		const int n = 6 + (int)(rnd() % 50);
+		const int mode = iter % 6;
+		std::vector<short> a(n), b(n);
+		if (mode < 3) {  // coefficients of a smooth-ish signal: forward-transform bounded data, perturb a little
+			const int amp = mode == 0 ? 2048 : mode == 1 ? 1000 : 300;
+			for (int i = 0; i < n; i++) { a[i] = (short)((int)(rnd() % (2 * amp)) - amp); b[i] = (short)((i * 37 % (2 * amp)) - amp); }
+			ref_line(a); ref_line(b);
+			for (int i = 0; i < n; i++) { a[i] += (short)((int)(rnd() % 9) - 4); b[i] += (short)((int)(rnd() % 65) - 32); }
+		} else {
+			const int amp = mode == 3 ? 8191 : mode == 4 ? 3000 : 600;  // arbitrary coefficients, up to the bound itself
+			for (int i = 0; i < n; i++) { a[i] = (short)((int)(rnd() % (2 * amp + 1)) - amp); b[i] = (short)((rnd() & 1) ? amp : -amp); }
+		}
+		std::vector<unsigned> X(n);
+		for (int i = 0; i < n; i++) X[i] = enc(a[i], b[i], G);
+		const bool ok = packed_line_inv(X);
+		if (!ok) { rejected++; continue; }
+		used++;
+		ref_line_inv(a); ref_line_inv(b);
+		for (int i = 0; i < n; i++)
+			CHECK(dec_lo(X[i], G) == a[i] && dec_hi(X[i], G) == b[i], "inverse n=%d i=%d mode=%d: got (%d,%d) want (%d,%d)", n, i, mode,
+			      dec_lo(X[i], G), dec_hi(X[i], G), a[i], b[i]);
+	}
+	printf("inverse lines that passed the guard: %d (rejected %d)\n", used, rejected);
+	CHECK(used > 8000 && rejected > 1000, "inverse test mix is off");
+	// the guard is exactly the range test
+	for (int v = -32768; v <= 32767; v++) {
+		const bool in = v >= -8192 && v <= 8191;
+		CHECK(((enc(v, 0, G) & GUARD_I) == 0) == in && ((enc(0, v, G) & GUARD_I) == 0) == in, "GUARD_I v=%d", v);
+	}
+	// dequantisation
+	for (int i = 0; i < 200000; i++) {
+		const int q = 1 + (int)(rnd() % 700), lim = 8191 / q;
+		const int c0 = (int)(rnd() % (2 * lim + 1)) - lim, c1 = (int)(rnd() % (2 * lim + 1)) - lim;
+		const unsigned c2 = (unsigned)(c0 & 0xFFFF) | (unsigned)c1 << 16;
+		const unsigned r = dequant(c2, (unsigned)q, G - OB * (unsigned)q);
+		CHECK(dec_lo(r, G) == c0 * q && dec_hi(r, G) == c1 * q && (r & GUARD_I) == 0, "dequant %d %d q %d", c0, c1, q);
+	}
+}
+
+static int clip255(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+static void test_pixels()
+{
+	for (int i = 0; i < 400000; i++) {
+		int v[2][3];
+		for (int h = 0; h < 2; h++)
+			for (int c = 0; c < 3; c++) v[h][c] = (i % 3 == 0) ? ((rnd() & 1) ? 8191 : -8192) : (int)(rnd() % 16384) - 8192;
+		unsigned r, g, b;
+		ycocg_out(enc(v[0][0], v[1][0], G), enc(v[0][1], v[1][1], G), enc(v[0][2], v[1][2], G), r, g, b);
+		for (int h = 0; h < 2; h++) {
+			short co = (short)v[h][0], cg = (short)v[h][1], y = (short)v[h][2];  // ric.cpp:98-110
+			co = (co + 4) >> 3; cg = (cg + 4) >> 3; y = (y + 8) >> 4;
+			y -= (cg >> 1) - 128;
+			cg += y;
+			y -= co >> 1;
+			co += y;
+			const int R = clip255(co), Gv = clip255(cg), B = clip255(y);
+			const int gr = (r >> (16 * h)) & 0xFF, gg = (g >> (16 * h)) & 0xFF, gb = (b >> (16 * h)) & 0xFF;
+			CHECK(gr == R && gg == Gv && gb == B, "ycocg half %d in (%d,%d,%d): got (%d,%d,%d) want (%d,%d,%d)", h, v[h][0], v[h][1], v[h][2], gr, gg, gb, R, Gv, B);
+			CHECK(((r >> (16 * h)) & 0xFF00) == 0x4100 && ((g >> (16 * h)) & 0xFF00) == 0x4100 && ((b >> (16 * h)) & 0xFF00) == 0x4100, "pixel constant");
+		}
+		const unsigned go = gray_out(enc(v[0][0], v[1][0], G));
+		for (int h = 0; h < 2; h++)
+			CHECK((int)((go >> (16 * h)) & 0xFF) == clip255(128 + ((v[h][0] + 8) >> 4)), "gray %d", v[h][0]);
+	}
+}
+
 int main()
 {
+	test_inverse();
+	test_pixels();
 	test_rows();
 	test_cols();
 	test_guard();
