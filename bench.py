@@ -699,6 +699,10 @@ def run_ours(args):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()  # a crash inside the C-ABI names the Python frame that made the call
+    if os.environ.get("RIC_SEGV_BT"):  # debug aid (scripts/debug/segv_bt.c): native backtrace instead
+        ctypes.CDLL(os.environ["RIC_SEGV_BT"]).segv_bt_install()
     args = parse()
     if args.gpus > 1 and "RANK" not in os.environ:  # convenience: re-launch under torchrun
         port = str(29500 + os.getpid() % 2000)

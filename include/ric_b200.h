@@ -96,6 +96,7 @@ int ric_decode_u8(ric_ctx *ctx, const void *arenas, int n, int q, uint8_t *dst);
  * ric_encode_u8_stream returns as soon as every chunk of the batch is enqueued (H2D, kernels, D2H
  * alternate over three internal streams).  `done(user, first_image, n_images)` is called once per
  * chunk, from a CUDA callback thread, when the arenas of those images have landed in `arenas`
+ * (chunks alternate over three streams and may complete OUT OF ORDER: act on exactly [first, first + n))
  * (use pinned memory, ric_host_alloc): the callback must not call CUDA or ric_* functions -- it
  * hands the chunk to a host worker, e.g. one running the reference's entropy half of CodeBand
  * (wavelet2d.cpp:119-159) while the GPU works on the next chunk.  ric_sync waits for everything.

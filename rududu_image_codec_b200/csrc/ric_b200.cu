@@ -21,6 +21,7 @@
 #include "ric_fwd.cuh"
 #include "ric_fwd0.cuh"
 #include "ric_host.h"
+#include "ric_landed.h"
 #include "ric_inv.cuh"
 #include "ric_inv0.cuh"
 
@@ -1491,30 +1492,6 @@ static int worker_count(int threads, int n)
 	return std::max(1, std::min(threads, n));
 }
 
-namespace {
-struct LandedQueue {  // images whose arenas have reached pinned memory, in arrival order
-	std::mutex mu;
-	std::condition_variable cv;
-	int ready = 0, next = 0, total = 0;
-	static void landed(void *user, int first, int count)  // CUDA callback thread: no CUDA calls here
-	{
-		LandedQueue *q = (LandedQueue *)user;
-		{ std::lock_guard<std::mutex> l(q->mu); q->ready = std::max(q->ready, first + count); }
-		q->cv.notify_all();
-	}
-	void release_all() { { std::lock_guard<std::mutex> l(mu); ready = total; } cv.notify_all(); }
-	int take()  // next image index, or -1 when all have been handed out
-	{
-		std::unique_lock<std::mutex> l(mu);
-		cv.wait(l, [&] { return next < ready || next >= total; });
-		if (next >= total) return -1;
-		const int i = next++;
-		if (next >= total) cv.notify_all();  // workers still waiting have nothing left to wait for
-		return i;
-	}
-};
-}  // namespace
-
 int ric_compress_u8(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *files, size_t stride, size_t *sizes, int threads)
 {
 	int rc = check_batch(c, n, q, "ric_compress_u8");
@@ -1533,7 +1510,7 @@ int ric_compress_u8(ric_ctx *c, const uint8_t *src, int n, int q, uint8_t *files
 	for (int t = 0; t < nw; t++)
 		pool.emplace_back([&] {
 			for (int i; (i = queue.take()) >= 0;) {
-				if (cancelled) continue;  // the GPU stage failed: nothing valid to code, just drain the queue
+				if (cancelled) break;  // the GPU stage failed: nothing valid to code
 				uint8_t *f = files + (size_t)i * stride;
 				ric_header_write(f, g.width, g.height, q, g.channels == 3, g.trans);
 				const long sz = entropy_encode_image(g, c->h_stage + (size_t)i * img_ar, f + RIC_HEADER_BYTES, stride - RIC_HEADER_BYTES);

@@ -202,6 +202,7 @@ public:
 	}
 
 	RIC_HD bool overflow() const { return overflow_; }
+	RIC_HD void poison() { overflow_ = true; }  // input that no encode stage produces: the call reports failure
 	uint8_t lead(int i) const { return lead_[i]; }
 
 private:
@@ -627,6 +628,8 @@ RIC_HD inline unsigned code_block(Port &io, GeomModel &geo, C *blk, int stride, 
 				for (int x = 0; x < w; x++, i++) mask |= (uint32_t)(r[x] != 0) << i;
 		}
 		k = (unsigned)count_ones(mask);
+		if constexpr (Port::writing)
+			if (FINE && k == 0) { io.m.poison(); return 0; }  // an all-zero block without the INSIGNIF_BLOCK mark: malformed arena
 	}
 	if (full) {
 		if constexpr (Port::writing) {
@@ -874,6 +877,7 @@ RIC_HD void walk_band_hinted(WPort &io, const C *base, const ric_band_info &b, c
 				const int table = (kmean[ctx] + (1 << 9)) >> 10;
 				const uint32_t mask = hint.a & 0xFFFFu;
 				const unsigned k = (unsigned)count_ones(mask);
+				if (FINE && k == 0) { io.m.poison(); continue; }  // malformed arena (see code_block)
 				const CountCode &c = FINE ? T.fine[table] : T.low[table];
 				const unsigned s = FINE ? k - 1 : k;
 				io.bits(c.code[s], c.len[s]);

@@ -18,6 +18,8 @@ with open(os.path.join(P, "%s_bench_ncu_full_summary.txt" % tag), "w") as f:
 rows = list(csv.reader(open(raw))); hdr, units = rows[0], rows[1]; idx = {h: i for i, h in enumerate(hdr)}
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
 def val(r, k): return float(r[idx[k]]) * scale[units[idx[k]]]
+tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+def val_t(r): return float(r[idx["gpu__time_duration.sum"]]) * tscale.get(units[idx["gpu__time_duration.sum"]], 1.0)
 bench = json.load(open(os.path.join(G, "bench_%s_final.json" % tag)))
 B = bench["config"]["batch_per_gpu"]
 out = {"source": "ncu --set full --clock-control none on `bench.py --steps 2 --warmup 3` (batch %d x 3840x2160 RGB); "
@@ -31,14 +33,22 @@ for r in rows[2:]:
          "dram_pct": float(r[idx["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]])}
     e["dram_bytes_per_launch"] = e["dram_read_bytes"] + e["dram_write_bytes"]
     out["kernels"].append(e)
+    if "smsp__inst_executed.sum" in idx:
+        e["warp_inst"] = float(r[idx["smsp__inst_executed.sum"]])
+    e["duration_us"] = val_t(r)
     if "fwd_level_kernel<1, 0, 1>" in name:
         out["fwd_level0_bytes_per_launch"] = e["dram_bytes_per_launch"]
         out["fwd_level0_samples_per_launch"] = B * 3840 * 2160 * 3
+        if "warp_inst" in e:  # thread-instructions per sample = 32 x warp instructions / samples (VERDICT r1 item 1's figure)
+            out["fwd_level0_thread_inst_per_sample"] = round(32 * e["warp_inst"] / out["fwd_level0_samples_per_launch"], 2)
         out["fwd_level0_issue_active_pct"], out["fwd_level0_alu_pipe_pct"] = e["issue_active_pct"], e["alu_pipe_pct"]
         out["limiter"] = ("integer issue: ncu ALU pipe %.0f %%, issue slots %.0f %%, DRAM %.0f %% of peak (level-0 forward kernel)"
                           % (e["alu_pipe_pct"], e["issue_active_pct"], e["dram_pct"]))
     if "inv_level_kernel<1, 0, 2>" in name:
         out["inv_level0_bytes_per_launch"] = e["dram_bytes_per_launch"]
+        out["inv_level0_issue_active_pct"], out["inv_level0_alu_pipe_pct"] = e["issue_active_pct"], e["alu_pipe_pct"]
+        if "warp_inst" in e:
+            out["inv_level0_thread_inst_per_sample"] = round(32 * e["warp_inst"] / (B * 3840 * 2160 * 3), 2)
 json.dump(out, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 
 lrows = list(csv.reader(l for l in open(os.path.join(G, "launches_%s.csv" % tag)) if l.startswith('"')))

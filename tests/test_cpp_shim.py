@@ -51,6 +51,16 @@ def test_codec_call_sequence_matches_oracle(tmp_path, w, h, ch, q):
         assert np.array_equal(got[p], o.inverse(a)), p
 
 
+def test_landed_queue_out_of_order_chunks(tmp_path):
+    """ric_compress_u8's hand-off to its entropy workers: chunks land out of order (three streams); no image may be
+    handed out before its own chunk has landed (regression: the queue once summarised arrivals as a high-water mark)."""
+    exe = str(tmp_path / "landed_test")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-pthread", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "landed_test.cpp")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+
+
 def test_shim_compiles_and_fails_loudly_without_gpu(tmp_path):
     import torch
     exe = _build(tmp_path)

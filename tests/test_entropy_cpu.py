@@ -85,6 +85,15 @@ def test_encoder_reports_small_buffer():
     assert e.value.code == capi.E_NOMEM
 
 
+@pytest.mark.parametrize("hinted", [False, True])
+def test_encoder_rejects_arena_without_block_marks(hinted):
+    """An arena no encode stage produces (all-zero blocks that lack the INSIGNIF_BLOCK mark, e.g. a staging buffer
+    read before its copy landed) makes the coder report failure instead of indexing its count tables at -1."""
+    o = oraclebind.Oracle(128, 128, 5)
+    with pytest.raises(capi.RicError):
+        capi.entropy_encode(128, 128, 1, np.zeros(o.arena_bytes, dtype=np.uint8), hinted=hinted)
+
+
 def test_decoder_rejects_truncated_payload():
     img = _image(128, 128, 1)
     o = oraclebind.Oracle(128, 128, 5)
