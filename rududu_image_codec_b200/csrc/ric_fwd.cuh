@@ -102,10 +102,15 @@ __device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const void *base, lon
 	}
 }
 
-__device__ __forceinline__ int byte_of(unsigned lo, unsigned hi, int k)
+// c + mult * (byte k & 3 of word): one IDP.4A (u8 x s8 dot product, FMA pipe; scripts/ubench/pipes3.cu).
+// mult in [-128, 127], compile-time or warp-uniform; the byte position is a compile-time shift.
+__device__ __forceinline__ int dp4a_pick(unsigned word, int mult, int k, int c)
 {
-	return (int)__byte_perm(k < 4 ? lo : hi, 0, 0x4440 | (k & 3));
+	int d;
+	asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(word), "r"((int)((unsigned)(mult & 0xFF) << (8 * (k & 3)))), "r"(c));
+	return d;
 }
+
 
 // raw registers -> 8 level-input samples (colour transform / level shift fused here).
 // `plane` is warp-uniform: each branch computes only what its plane needs.
@@ -113,25 +118,39 @@ template <int SRC>
 __device__ __forceinline__ void convert_raw(const RawRow<SRC> &raw, int (&v)[8], int plane, int shift)
 {
 	if (SRC == SRC_U8_GRAY) {
-		const int sh = shift ? 4 : 0;
 #pragma unroll
-		for (int k = 0; k < 8; k++) v[k] = (byte_of(raw.r[0], raw.r[1], k) - 128) << sh;  // ric.cpp:144 / :147
+		for (int k = 0; k < 8; k++) v[k] = dp4a_pick(raw.r[k >> 2], 16, k, -2048);  // (pixel - 128) << 4, ric.cpp:147
+		if (!shift) {  // ric.cpp:144 (q == 0): no up-shift
+#pragma unroll
+			for (int k = 0; k < 8; k++) v[k] >>= 4;
+		}
 	} else if (SRC == SRC_U8_RGB) {
-		// RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y).  The three planes share one copy of
-		// the lifting chain Co -> t -> Cg -> Y; each warp stops where its plane is reached (warp-uniform).
-#pragma unroll
-		for (int k = 0; k < 8; k++) v[k] = byte_of(raw.r[0], raw.r[1], k) - byte_of(raw.r[4], raw.r[5], k);  // Co = R - B
-		if (plane > 0) {
+		// RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y): Co = R - B, t = B + (Co >> 1), Cg = G - t,
+		// Y = t + (Cg >> 1) - 128, then << 3 (chroma) / << 4 (luma) when `shift`.
+		{
+			// Closed forms (floors of integers nest: t = (R + B) >> 1, Y + 128 = (R + 2G + B) >> 2), each a dot
+			// product of the pixel bytes with small constants plus masks -- IDP.4A picks the byte, scales it and
+			// accumulates in one FMA-pipe instruction, so no byte extraction and no shifts on the ALU pipe:
+			//   Co << 3 = 8R - 8B
+			//   Cg << 3 = 8G + ((7 - 4R - 4B) & ~7)        (-(n & ~7) = (7 - n) & ~7 for n = 4(R + B))
+			//   Y  << 4 = (4R + 8G + 4B - 2048) & ~15
+			// One instruction sequence serves the three planes -- ((aR*R + aB*B + c) & m1) + aG*G) & m2 with
+			// warp-uniform constants -- which keeps the loop free of per-plane branches and its code small
+			// (the kernel is instruction-fetch sensitive: profiles/README.md, round 2).
+			const int aR = plane == 0 ? 8 : plane == 1 ? -4 : 4, aB = plane == 0 ? -8 : plane == 1 ? -4 : 4;
+			const int aG = plane == 0 ? 0 : 8, c = plane == 0 ? 0 : plane == 1 ? 7 : -2048;
+			const int m1 = plane == 1 ? ~7 : ~0, m2 = plane == 2 ? ~15 : ~0;
 #pragma unroll
 			for (int k = 0; k < 8; k++) {
-				const int t = byte_of(raw.r[4], raw.r[5], k) + (v[k] >> 1);   // t = B + (Co >> 1)
-				const int cg = byte_of(raw.r[2], raw.r[3], k) - t;             // Cg = G - t
-				v[k] = plane == 2 ? t + ((cg >> 1) - 128) : cg;                // Y = t + (Cg >> 1) - 128
+				const int in = dp4a_pick(raw.r[k >> 2], aR, k, dp4a_pick(raw.r[4 + (k >> 2)], aB, k, c)) & m1;
+				v[k] = dp4a_pick(raw.r[2 + (k >> 2)], aG, k, in) & m2;
 			}
 		}
-		const int sh = shift ? (plane == 2 ? 4 : 3) : 0;
+		if (!shift) {  // q == 0 (lossless): no up-shift -- the shifted values are exact multiples, shift them back (warp-uniform, rare)
+			const int sh = plane == 2 ? 4 : 3;
 #pragma unroll
-		for (int k = 0; k < 8; k++) v[k] <<= sh;
+			for (int k = 0; k < 8; k++) v[k] >>= sh;
+		}
 	} else if (SRC == SRC_S16) {
 #pragma unroll
 		for (int k = 0; k < 8; k++) {
@@ -371,6 +390,9 @@ struct RegIO {
 };
 
 // RingT: anything with `uint2 v[3][RR][32]` (RR rows per band, a power of two); bands [o_begin, o_end).
+#ifndef RIC_EXP_FLATQ
+#define RIC_EXP_FLATQ true  // level kernels: quantise the block in registers (false: rolled loops over the shared-memory ring)
+#endif
 template <int RR, bool FLAT = true, class RingT>
 __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &rg, KeyRows &keys, char *arena,
                                                     unsigned char *flags, const QuantBand *qb3, int bx, int by, int lane,
@@ -387,7 +409,11 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 		RegIO io;  // FLAT: the block stays in registers from here to the band stores
 #pragma unroll
 		for (int r = 0; r < 4; r++) io.rows[r] = rg.v[o][(y0 + r) & (RR - 1)][lane];
+#ifdef RIC_EXP_NOQUANT  // diagnosis only (wrong results): how fast is the kernel without the quantiser's code?
+		if (false) {
+#else
 		if (P.quant) {
+#endif
 			const QuantBand *qb = qb3 + o;
 			const bool full = bw == 4 && bh == 4;
 			const int T = full ? qb->T : qb->Te;
@@ -575,7 +601,7 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<S
 		if ((jv & 3) == 3) {  // block row jv>>2 of D, H and V is complete (D/H rows sit one slot ahead in the ring)
 			const int by = jv >> 2;
 			if (by >= (y0 >> 3)) {
-				if constexpr (SH) flush_blocks_packed<RING_ROWS>(P, rg, keys, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
+				if constexpr (SH) flush_blocks_packed<RING_ROWS, RIC_EXP_FLATQ>(P, rg, keys, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
 				else flush_blocks<SH>(P, rg, arena, flags, &s_qb[cls][0], bx, by, lane, lane_out);
 			}
 		}

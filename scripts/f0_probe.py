@@ -3,6 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np, torch
 from rududu_image_codec_b200 import capi
+if os.environ.get("RIC_LIB"):  # A/B timing of a variant build (scripts/build_variant.sh)
+    capi.LIB_PATH = os.path.abspath(os.environ["RIC_LIB"])
 from rududu_image_codec_b200.synth import synth_image
 
 def run(w, h, ch, levels, n, q=9):
@@ -18,10 +20,15 @@ def run(w, h, ch, levels, n, q=9):
         c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
     torch.cuda.synchronize()
     c.path_stats()
-    c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
-    torch.cuda.synchronize()
-    print("%dx%dx%d n=%d q=%d FWD0=%s: level ms %s path stats %s" % (w, h, ch, n, q, os.environ.get("RIC_FWD0", "1"),
-          ["%.3f" % t for t in c.level_times(0)], c.path_stats()), flush=True)
+    runs = []
+    for _ in range(9):  # median of 9 calls per level: single calls scatter by about 2 %
+        c.encode_u8_device(src.data_ptr(), pitch, n, q, ar.data_ptr(), st)
+        torch.cuda.synchronize()
+        runs.append(c.level_times(0))
+    med = [sorted(r[k] for r in runs)[len(runs) // 2] for k in range(len(runs[0]))]
+    print("%dx%dx%d n=%d q=%d FWD0=%s: level ms (median of 9) %s  level-0 min %.3f max %.3f" % (
+          w, h, ch, n, q, os.environ.get("RIC_FWD0", "0"), ["%.3f" % t for t in med],
+          min(r[0] for r in runs), max(r[0] for r in runs)), flush=True)
     c.close()
 
 if __name__ == "__main__":

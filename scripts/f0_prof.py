@@ -3,6 +3,8 @@ import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np, torch
 from rududu_image_codec_b200 import capi
+if os.environ.get("RIC_LIB"):  # A/B profiling of a variant build (scripts/build_variant.sh)
+    capi.LIB_PATH = os.path.abspath(os.environ["RIC_LIB"])
 from rududu_image_codec_b200.synth import synth_image
 w, h, ch, levels, n, q = 3840, 2160, 3, 5, int(os.environ.get("N", "16")), 9
 imgs = np.stack([synth_image(i, w, h, ch) for i in range(4)])
