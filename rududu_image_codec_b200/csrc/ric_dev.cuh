@@ -23,6 +23,20 @@ constexpr unsigned FULL = 0xffffffffu;
 template <bool SH>
 __device__ __forceinline__ int TR(int v) { return SH ? (int)(short)v : v; }
 
+// The same store-to-C truncation on the FMA pipe: IDP.2A.LO.S16.U8 with the byte pair (1, 0) sign-extends the low
+// half.  The inverse kernels use it (their ALU pipe is the busier one: -4 % per launch, measured); the forward
+// kernels keep the ALU form (their FMA pipe already carries the quantiser's multiplies: +2 % with this form).
+template <bool SH>
+__device__ __forceinline__ int TRI(int v)
+{
+	if (SH) {
+		int d;
+		asm("dp2a.lo.s32.u32 %0, %1, 1, 0;" : "=r"(d) : "r"(v));
+		return d;
+	}
+	return v;
+}
+
 __device__ __forceinline__ int m08i(int a)  // mult08<int>, wavelet2d.cpp:307-318
 {
 	a -= a >> 2;
@@ -36,6 +50,13 @@ __device__ __forceinline__ int m08c(int a)  // mult08<C>: every assignment trunc
 	a = TR<SH>(a - (a >> 2));
 	a = TR<SH>(a + (a >> 4));
 	return TR<SH>(a + (a >> 8));
+}
+template <bool SH>
+__device__ __forceinline__ int m08ci(int a)  // the same for the inverse kernels (TRI)
+{
+	a = TRI<SH>(a - (a >> 2));
+	a = TRI<SH>(a + (a >> 4));
+	return TRI<SH>(a + (a >> 8));
 }
 
 // ---- forward lifting steps (Appendix A.1 / A.3).  x: centre, l/r: neighbours (proper C values).
@@ -90,40 +111,40 @@ __device__ __forceinline__ int fS4_last(int x, int l)
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU4(int x, int l, int r)
 {
-	if (TRANS == T97) { int t = TR<SH>(l + r); return TR<SH>(x - ((t >> 1) - (t >> 5))); }
+	if (TRANS == T97) { int t = TRI<SH>(l + r); return TRI<SH>(x - ((t >> 1) - (t >> 5))); }
 	return x;
 }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU4_last(int x, int l)
 {
 	if (TRANS != T97) return x;
-	l = TR<SH>(l);  // row pass: vertical U1 results arrive un-truncated
-	return TR<SH>(x - (l - (l >> 4)));
+	l = TRI<SH>(l);  // row pass: vertical U1 results arrive un-truncated
+	return TRI<SH>(x - (l - (l >> 4)));
 }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int iU3(int x, int l, int r) { return TRANS == T97 ? TR<SH>(x - m08i(l + r)) : x; }
+__device__ __forceinline__ int iU3(int x, int l, int r) { return TRANS == T97 ? TRI<SH>(x - m08i(l + r)) : x; }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int iU3_edge(int x, int n) { return TRANS == T97 ? TR<SH>(x - 2 * m08c<SH>(n)) : x; }
+__device__ __forceinline__ int iU3_edge(int x, int n) { return TRANS == T97 ? TRI<SH>(x - 2 * m08ci<SH>(n)) : x; }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU2(int x, int l, int r)
 {
 	if (TRANS == T97) return x + ((l + r) >> 4);
-	if (TRANS == THAAR) return TR<SH>(x - (l >> 1));  // i[1] -= i[0] >> 1, wavelet2d.cpp:784
-	return TR<SH>(x - ((l + r) >> 2));  // 5/3: feeds the un-truncated (l + r) >> 1 of U1
+	if (TRANS == THAAR) return TRI<SH>(x - (l >> 1));  // i[1] -= i[0] >> 1, wavelet2d.cpp:784
+	return TRI<SH>(x - ((l + r) >> 2));  // 5/3: feeds the un-truncated (l + r) >> 1 of U1
 }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int iU2_last(int x, int l) { return TRANS == T97 ? TR<SH>(x + (l >> 3)) : TR<SH>(x - (l >> 1)); }
+__device__ __forceinline__ int iU2_last(int x, int l) { return TRANS == T97 ? TRI<SH>(x + (l >> 3)) : TRI<SH>(x - (l >> 1)); }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU1(int x, int l, int r)
 {
-	if (TRANS == T97) { int t = TR<SH>(l + r); return x + (t + (t >> 1)); }
-	if (TRANS == THAAR) return TR<SH>(x + r);  // i[0] += i[1], wavelet2d.cpp:785
-	return TR<SH>(x + ((l + r) >> 1));
+	if (TRANS == T97) { int t = TRI<SH>(l + r); return x + (t + (t >> 1)); }
+	if (TRANS == THAAR) return TRI<SH>(x + r);  // i[0] += i[1], wavelet2d.cpp:785
+	return TRI<SH>(x + ((l + r) >> 1));
 }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int iU1_first(int x, int r) { return TRANS == T97 ? TR<SH>(x + 3 * r) : TR<SH>(x + r); }
+__device__ __forceinline__ int iU1_first(int x, int r) { return TRANS == T97 ? TRI<SH>(x + 3 * r) : TRI<SH>(x + r); }
 template <bool SH, int TRANS>
-__device__ __forceinline__ int iU1_last(int x, int l) { return TRANS == T97 ? TR<SH>(x + 3 * l) : TR<SH>(x + l); }
+__device__ __forceinline__ int iU1_last(int x, int l) { return TRANS == T97 ? TRI<SH>(x + 3 * l) : TRI<SH>(x + l); }
 
 // ---- horizontal passes on the 8 columns a lane holds (cb = absolute column of v[0], even).
 // Neighbours across lanes come from warp shuffles.  Every element is first computed with the

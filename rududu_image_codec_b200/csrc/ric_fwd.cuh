@@ -112,8 +112,71 @@ __device__ __forceinline__ int dp4a_pick(unsigned word, int mult, int k, int c)
 }
 
 
+// Per-plane constants of the RGB closed forms below, one row per plane in shared memory (filled once per CTA):
+// the byte-position-shifted multipliers of R, B and G, then {c, m1, m2, down-shift for q == 0}.  Read back with
+// four 128-bit loads per row pair: kept in registers across the loop they would cost 16 registers, recomputed
+// from `plane` they cost 2 instructions per sample (both measured).
+struct ColourTab { int4 aR, aB, aG, cm; };
+
+__device__ __forceinline__ void colour_tab_fill(ColourTab *tab, int shift)  // tab[3], any thread layout
+{
+	for (int i = threadIdx.x; i < 3 * 16; i += blockDim.x) {
+		const int plane = i >> 4, j = i & 15;
+		const int aR = plane == 0 ? 8 : plane == 1 ? -4 : 4, aB = plane == 0 ? -8 : plane == 1 ? -4 : 4, aG = plane == 0 ? 0 : 8;
+		int v;
+		if (j < 12) v = (int)((unsigned)((j < 4 ? aR : j < 8 ? aB : aG) & 0xFF) << (8 * (j & 3)));
+		else v = j == 12 ? (plane == 0 ? 0 : plane == 1 ? 7 : -2048) : j == 13 ? (plane == 1 ? ~7 : ~0) : j == 14 ? (plane == 2 ? ~15 : ~0)
+		                 : (shift ? 0 : plane == 2 ? 4 : 3);
+		((int *)tab)[i] = v;
+	}
+}
+
+__device__ __forceinline__ int4 lds_v4(const int4 *p)  // volatile: reloaded where it is used, never hoisted out of the row loop
+{
+	int4 r;
+	asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+	return r;
+}
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)  // IDP.4A.U8.S8: c + sum of a.u8[i] * b.s8[i]
+{
+	int d;
+	asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
+// RGBtoYCoCg<shift> (ric.cpp:76-91; planes 0 Co, 1 Cg, 2 Y) of two rows of 8 pixels.  The reference's lifting chain
+// Co = R - B, t = B + (Co >> 1), Cg = G - t, Y = t + (Cg >> 1) - 128, then << 3 (chroma) / << 4 (luma), has closed
+// forms, because floors of integers nest (t = (R + B) >> 1, Y + 128 = (R + 2G + B) >> 2):
+//   Co << 3 = 8R - 8B
+//   Cg << 3 = 8G + ((7 - 4R - 4B) & ~7)        (-(n & ~7) = (7 - n) & ~7 for n = 4(R + B))
+//   Y  << 4 = (4R + 8G + 4B - 2048) & ~15
+// (checked over all 2^24 pixels in tests/test_host_logic.py).  Each is a dot product of pixel bytes with small
+// constants plus masks: IDP.4A picks the byte, scales it and accumulates in ONE FMA-pipe instruction -- no byte
+// extraction and no shifts on the ALU pipe.  One sequence, ((aR*R + aB*B + c) & m1) + aG*G) & m2, serves the three
+// planes with the warp's constants from `tab`: no per-plane branches, small code (the kernel is
+// instruction-fetch sensitive: profiles/README.md, round 2).  q == 0 (no up-shift): the values are exact multiples
+// and are shifted back down.
+__device__ __forceinline__ void convert_rgb2(const RawRow<SRC_U8_RGB> &rawE, const RawRow<SRC_U8_RGB> &rawO, int (&ve)[8], int (&vo)[8],
+                                             const ColourTab *tab)
+{
+	const int4 aR = lds_v4(&tab->aR), aB = lds_v4(&tab->aB), aG = lds_v4(&tab->aG), cm = lds_v4(&tab->cm);
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		const int j = k & 3;
+		const int sR = j == 0 ? aR.x : j == 1 ? aR.y : j == 2 ? aR.z : aR.w, sB = j == 0 ? aB.x : j == 1 ? aB.y : j == 2 ? aB.z : aB.w;
+		const int sG = j == 0 ? aG.x : j == 1 ? aG.y : j == 2 ? aG.z : aG.w;
+		ve[k] = dp4a_us(rawE.r[2 + (k >> 2)], sG, dp4a_us(rawE.r[k >> 2], sR, dp4a_us(rawE.r[4 + (k >> 2)], sB, cm.x)) & cm.y) & cm.z;
+		vo[k] = dp4a_us(rawO.r[2 + (k >> 2)], sG, dp4a_us(rawO.r[k >> 2], sR, dp4a_us(rawO.r[4 + (k >> 2)], sB, cm.x)) & cm.y) & cm.z;
+	}
+	if (cm.w) {  // warp-uniform, rare
+#pragma unroll
+		for (int k = 0; k < 8; k++) { ve[k] >>= cm.w; vo[k] >>= cm.w; }
+	}
+}
+
 // raw registers -> 8 level-input samples (colour transform / level shift fused here).
-// `plane` is warp-uniform: each branch computes only what its plane needs.
+// (RGB sources go through convert_rgb2 above.)
 template <int SRC>
 __device__ __forceinline__ void convert_raw(const RawRow<SRC> &raw, int (&v)[8], int plane, int shift)
 {
@@ -123,33 +186,6 @@ __device__ __forceinline__ void convert_raw(const RawRow<SRC> &raw, int (&v)[8],
 		if (!shift) {  // ric.cpp:144 (q == 0): no up-shift
 #pragma unroll
 			for (int k = 0; k < 8; k++) v[k] >>= 4;
-		}
-	} else if (SRC == SRC_U8_RGB) {
-		// RGBtoYCoCg<shift>, ric.cpp:76-91 (planes 0 Co, 1 Cg, 2 Y): Co = R - B, t = B + (Co >> 1), Cg = G - t,
-		// Y = t + (Cg >> 1) - 128, then << 3 (chroma) / << 4 (luma) when `shift`.
-		{
-			// Closed forms (floors of integers nest: t = (R + B) >> 1, Y + 128 = (R + 2G + B) >> 2), each a dot
-			// product of the pixel bytes with small constants plus masks -- IDP.4A picks the byte, scales it and
-			// accumulates in one FMA-pipe instruction, so no byte extraction and no shifts on the ALU pipe:
-			//   Co << 3 = 8R - 8B
-			//   Cg << 3 = 8G + ((7 - 4R - 4B) & ~7)        (-(n & ~7) = (7 - n) & ~7 for n = 4(R + B))
-			//   Y  << 4 = (4R + 8G + 4B - 2048) & ~15
-			// One instruction sequence serves the three planes -- ((aR*R + aB*B + c) & m1) + aG*G) & m2 with
-			// warp-uniform constants -- which keeps the loop free of per-plane branches and its code small
-			// (the kernel is instruction-fetch sensitive: profiles/README.md, round 2).
-			const int aR = plane == 0 ? 8 : plane == 1 ? -4 : 4, aB = plane == 0 ? -8 : plane == 1 ? -4 : 4;
-			const int aG = plane == 0 ? 0 : 8, c = plane == 0 ? 0 : plane == 1 ? 7 : -2048;
-			const int m1 = plane == 1 ? ~7 : ~0, m2 = plane == 2 ? ~15 : ~0;
-#pragma unroll
-			for (int k = 0; k < 8; k++) {
-				const int in = dp4a_pick(raw.r[k >> 2], aR, k, dp4a_pick(raw.r[4 + (k >> 2)], aB, k, c)) & m1;
-				v[k] = dp4a_pick(raw.r[2 + (k >> 2)], aG, k, in) & m2;
-			}
-		}
-		if (!shift) {  // q == 0 (lossless): no up-shift -- the shifted values are exact multiples, shift them back (warp-uniform, rare)
-			const int sh = plane == 2 ? 4 : 3;
-#pragma unroll
-			for (int k = 0; k < 8; k++) v[k] >>= sh;
 		}
 	} else if (SRC == SRC_S16) {
 #pragma unroll
@@ -486,7 +522,7 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 // One job = one (image, plane, row segment, strip); see the header comment.
 template <bool SH, int TRANS, int SRC>
 __device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<SH> &rg, KeyRows &keys,
-                                        const QuantBand (&s_qb)[2][3], int lane)
+                                        const QuantBand (&s_qb)[2][3], const ColourTab *ctab, int lane)
 {
 	// plane fastest: the planes of one RGB strip share their u8 loads through L1
 	const int plane = (int)(job % (unsigned)P.nplanes); job /= (unsigned)P.nplanes;  // (job ids fit 32 bits: host checks)
@@ -546,8 +582,8 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<S
 #pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
 		int ne[8], no[8];
-		convert_raw<SRC>(rawE, ne, plane, P.shift);
-		convert_raw<SRC>(rawO, no, plane, P.shift);
+		if constexpr (SRC == SRC_U8_RGB) convert_rgb2(rawE, rawO, ne, no, ctab + plane);
+		else { convert_raw<SRC>(rawE, ne, plane, P.shift); convert_raw<SRC>(rawO, no, plane, P.shift); }
 		{  // prefetch the next row pair
 			const int re = 2 * t + 2, ro = re + 1;
 			load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
@@ -622,7 +658,9 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 	__shared__ QuantBand s_qb[2][3];
 	__shared__ Ring<SH> s_ring[FWD_WARPS];
 	__shared__ KeyRows s_keys[SH ? FWD_WARPS : 1];
+	__shared__ ColourTab s_ctab[SRC == SRC_U8_RGB ? 3 : 1];
 	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
+	if (SRC == SRC_U8_RGB) colour_tab_fill(s_ctab, P.shift);
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const long long njobs = (long long)P.nstrips * P.nplanes * P.nsegs * P.nimages;
@@ -631,7 +669,7 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 		if (lane == 0) job = atomicAdd(P.counter, 1ull);
 		job = __shfl_sync(FULL, job, 0);
 		if ((long long)job >= njobs) break;
-		fwd_job<SH, TRANS, SRC>(P, (unsigned)job, s_ring[wib], s_keys[SH ? wib : 0], s_qb, lane);
+		fwd_job<SH, TRANS, SRC>(P, (unsigned)job, s_ring[wib], s_keys[SH ? wib : 0], s_qb, s_ctab, lane);
 	}
 }
 

@@ -127,10 +127,10 @@ __device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &
 	}
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
-		xe[2 * k] = TR<S>(d[k] * qd);
-		xe[2 * k + 1] = TR<S>(hh[k] * qh);
-		xo[2 * k] = TR<S>(v[k] * qv);
-		xo[2 * k + 1] = TR<S>(l[k] * ql);  // also the (C) narrowing of an int LL, wavelet2d.cpp:971-980
+		xe[2 * k] = TRI<S>(d[k] * qd);
+		xe[2 * k + 1] = TRI<S>(hh[k] * qh);
+		xo[2 * k] = TRI<S>(v[k] * qv);
+		xo[2 * k + 1] = TRI<S>(l[k] * ql);  // also the (C) narrowing of an int LL, wavelet2d.cpp:971-980
 	}
 }
 
@@ -227,7 +227,7 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 				unsigned b[8];
 #pragma unroll
 				for (int k = 0; k < 8; k++) {  // ric.cpp:229 / :237-240
-					int v = TR<SH>(o[k]);  // the last lifting step leaves its result un-truncated
+					int v = TRI<SH>(o[k]);  // the last lifting step leaves its result un-truncated
 					v = P.shift ? clip255((int)(short)(128 + ((v + 8) >> 4))) : (v + 128);
 					b[k] = (unsigned)v & 0xFF;
 				}
