@@ -65,13 +65,42 @@ __device__ __forceinline__ typename RawIn<SH>::vec ldvec(const char *rowp, int c
 	return z;
 }
 
+#ifndef RIC_EXP_UNPACK_DP2A
+#define RIC_EXP_UNPACK_DP2A 1
+#endif
+// halves of a packed pair, sign-extended on the FMA pipe (IDP.2A.LO.S16.U8 with the byte pairs (1, 0) / (0, 1))
+__device__ __forceinline__ int s16_lo_fma(unsigned w) { int d; asm("dp2a.lo.s32.u32 %0, %1, 0x0001, 0;" : "=r"(d) : "r"(w)); return d; }
+__device__ __forceinline__ int s16_hi_fma(unsigned w) { int d; asm("dp2a.lo.s32.u32 %0, %1, 0x0100, 0;" : "=r"(d) : "r"(w)); return d; }
+
+// sign-extended half `hi` of a packed pair plus a constant, one FMA-pipe instruction
+__device__ __forceinline__ int s16_plus(unsigned w, int hi, int c)
+{
+	int d;
+	if (hi) asm("dp2a.lo.s32.u32 %0, %1, 0x0100, %2;" : "=r"(d) : "r"(w), "r"(c));
+	else asm("dp2a.lo.s32.u32 %0, %1, 0x0001, %2;" : "=r"(d) : "r"(w), "r"(c));
+	return d;
+}
+// four ints clipped to 0..255 and packed, b0 in the low byte: two I2IP.U8.S32.SAT (d = c << 16 | sat(a) << 8 | sat(b))
+__device__ __forceinline__ unsigned pack4_sat(int b0, int b1, int b2, int b3)
+{
+	unsigned t, d;
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(b3), "r"(b2), "r"(0));
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(b1), "r"(b0), "r"(t));
+	return d;
+}
+
 template <bool SH>
 __device__ __forceinline__ void unpack4(const typename RawIn<SH>::vec &r, int (&o)[4])
 {
 	if (SH) {
 		const uint2 a = *(const uint2 *)&r;
+#if RIC_EXP_UNPACK_DP2A
+		o[0] = s16_lo_fma(a.x); o[1] = s16_hi_fma(a.x);
+		o[2] = s16_lo_fma(a.y); o[3] = s16_hi_fma(a.y);
+#else
 		o[0] = (int)(short)(a.x & 0xFFFF); o[1] = (int)a.x >> 16;
 		o[2] = (int)(short)(a.y & 0xFFFF); o[3] = (int)a.y >> 16;
+#endif
 	} else {
 		const int4 a = *(const int4 *)&r;
 		o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
@@ -122,8 +151,13 @@ __device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &
 	if (P.llsrc == LLSRC_S32 || (!SH && P.llsrc == LLSRC_BAND)) {
 		l[0] = in.l.x; l[1] = in.l.y; l[2] = in.l.z; l[3] = in.l.w;
 	} else {
+#if RIC_EXP_UNPACK_DP2A
+		l[0] = s16_lo_fma((unsigned)in.l.x); l[1] = s16_hi_fma((unsigned)in.l.x);
+		l[2] = s16_lo_fma((unsigned)in.l.y); l[3] = s16_hi_fma((unsigned)in.l.y);
+#else
 		l[0] = (int)(short)(in.l.x & 0xFFFF); l[1] = in.l.x >> 16;
 		l[2] = (int)(short)(in.l.y & 0xFFFF); l[3] = in.l.y >> 16;
+#endif
 	}
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
@@ -223,17 +257,22 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 					*(int4 *)dp = make_int4(o[0], o[1], o[2], o[3]);
 					*(int4 *)(dp + 4) = make_int4(o[4], o[5], o[6], o[7]);
 				}
-			} else {  // DST_U8_GRAY
-				unsigned b[8];
-#pragma unroll
-				for (int k = 0; k < 8; k++) {  // ric.cpp:229 / :237-240
-					int v = TRI<SH>(o[k]);  // the last lifting step leaves its result un-truncated
-					v = P.shift ? clip255((int)(short)(128 + ((v + 8) >> 4))) : (v + 128);
-					b[k] = (unsigned)v & 0xFF;
-				}
+			} else {  // DST_U8_GRAY, ric.cpp:229 / :237-240
 				unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + plane * P.dst_plane_stride +
 				                    (long long)row * P.dst_pitch + cb;
-				*(uint2 *)dp = make_uint2(pack4b(b[0], b[1], b[2], b[3]), pack4b(b[4], b[5], b[6], b[7]));
+				if (P.shift) {
+					// clip(128 + ((v + 8) >> 4)) with v the truncated lifting result: the truncation, the rounding
+					// constant and the + 128 (= 2048 >> 4) fold into one IDP.2A, the clip and the packing into I2IP
+					int b[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) b[k] = s16_plus((unsigned)o[k], 0, 8 + 2048) >> 4;
+					*(uint2 *)dp = make_uint2(pack4_sat(b[0], b[1], b[2], b[3]), pack4_sat(b[4], b[5], b[6], b[7]));
+				} else {
+					unsigned b[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++) b[k] = (unsigned)(TRI<SH>(o[k]) + 128) & 0xFF;
+					*(uint2 *)dp = make_uint2(pack4b(b[0], b[1], b[2], b[3]), pack4b(b[4], b[5], b[6], b[7]));
+				}
 			}
 		}
 		// rotate
@@ -254,36 +293,50 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 						if (!(row >= y0 && row < y1 && lane_out)) continue;
 						const uint4 c0 = (*stage)[set][my][0][half][lane], c1 = (*stage)[set][my][1][half][lane],
 						            c2 = (*stage)[set][my][2][half][lane];
-						unsigned R[8], G[8], B[8];
+						// YCoCgtoRGB<shift>, ric.cpp:93-112 (planes 0 Co, 1 Cg, 2 Y)
+						unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + (long long)row * P.dst_pitch + cb;
+						if (P.shift) {
+							// The rounding constants of the down-shifts -- and Y's + 128 = 2048 >> 4 -- ride on the
+							// IDP.2A that sign-extends each staged half; after the down-shifts every intermediate is
+							// < 2^14 in magnitude, so the reference's short stores cannot wrap; the clips to 0..255 and
+							// the byte packing are I2IP.U8.S32.SAT, two per four pixels.
+							int R[8], G[8], B[8];
 #pragma unroll
-						for (int k = 0; k < 8; k++) {  // YCoCgtoRGB<shift>, ric.cpp:93-112 (planes 0 Co, 1 Cg, 2 Y)
-							const unsigned w0 = k < 2 ? c0.x : k < 4 ? c0.y : k < 6 ? c0.z : c0.w;
-							const unsigned w1 = k < 2 ? c1.x : k < 4 ? c1.y : k < 6 ? c1.z : c1.w;
-							const unsigned w2 = k < 2 ? c2.x : k < 4 ? c2.y : k < 6 ? c2.z : c2.w;
-							int co = (k & 1) ? (int)w0 >> 16 : (int)(short)(w0 & 0xFFFF);
-							int cg = (k & 1) ? (int)w1 >> 16 : (int)(short)(w1 & 0xFFFF);
-							int y = (k & 1) ? (int)w2 >> 16 : (int)(short)(w2 & 0xFFFF);
-							if (P.shift) {
-								// after the down-shifts every intermediate is < 2^14 in magnitude: the reference's
-								// short stores cannot wrap, so no truncation is needed on this path
-								co = (co + 4) >> 3; cg = (cg + 4) >> 3; y = (y + 8) >> 4;
-								y -= (cg >> 1) - 128;
+							for (int k = 0; k < 8; k++) {
+								const unsigned w0 = k < 2 ? c0.x : k < 4 ? c0.y : k < 6 ? c0.z : c0.w;
+								const unsigned w1 = k < 2 ? c1.x : k < 4 ? c1.y : k < 6 ? c1.z : c1.w;
+								const unsigned w2 = k < 2 ? c2.x : k < 4 ? c2.y : k < 6 ? c2.z : c2.w;
+								int co = s16_plus(w0, k & 1, 4) >> 3, cg = s16_plus(w1, k & 1, 4) >> 3;
+								int y = s16_plus(w2, k & 1, 8 + 2048) >> 4;  // ((y + 8) >> 4) + 128
+								y -= cg >> 1;
 								cg += y;
 								y -= co >> 1;
 								co += y;
-								co = clip255(co); cg = clip255(cg); y = clip255(y);
-							} else {
+								R[k] = co; G[k] = cg; B[k] = y;
+							}
+							*(uint2 *)dp = make_uint2(pack4_sat(R[0], R[1], R[2], R[3]), pack4_sat(R[4], R[5], R[6], R[7]));
+							*(uint2 *)(dp + P.dst_plane_stride) = make_uint2(pack4_sat(G[0], G[1], G[2], G[3]), pack4_sat(G[4], G[5], G[6], G[7]));
+							*(uint2 *)(dp + 2 * P.dst_plane_stride) = make_uint2(pack4_sat(B[0], B[1], B[2], B[3]), pack4_sat(B[4], B[5], B[6], B[7]));
+						} else {  // q == 0: every store is a wrapping short store, no clip
+							unsigned R[8], G[8], B[8];
+#pragma unroll
+							for (int k = 0; k < 8; k++) {
+								const unsigned w0 = k < 2 ? c0.x : k < 4 ? c0.y : k < 6 ? c0.z : c0.w;
+								const unsigned w1 = k < 2 ? c1.x : k < 4 ? c1.y : k < 6 ? c1.z : c1.w;
+								const unsigned w2 = k < 2 ? c2.x : k < 4 ? c2.y : k < 6 ? c2.z : c2.w;
+								int co = (k & 1) ? (int)w0 >> 16 : (int)(short)(w0 & 0xFFFF);
+								int cg = (k & 1) ? (int)w1 >> 16 : (int)(short)(w1 & 0xFFFF);
+								int y = (k & 1) ? (int)w2 >> 16 : (int)(short)(w2 & 0xFFFF);
 								y = (int)(short)(y - ((cg >> 1) - 128));
 								cg = (int)(short)(cg + y);
 								y = (int)(short)(y - (co >> 1));
 								co = (int)(short)(co + y);
+								R[k] = (unsigned)co & 0xFF; G[k] = (unsigned)cg & 0xFF; B[k] = (unsigned)y & 0xFF;
 							}
-							R[k] = (unsigned)co & 0xFF; G[k] = (unsigned)cg & 0xFF; B[k] = (unsigned)y & 0xFF;
+							*(uint2 *)dp = make_uint2(pack4b(R[0], R[1], R[2], R[3]), pack4b(R[4], R[5], R[6], R[7]));
+							*(uint2 *)(dp + P.dst_plane_stride) = make_uint2(pack4b(G[0], G[1], G[2], G[3]), pack4b(G[4], G[5], G[6], G[7]));
+							*(uint2 *)(dp + 2 * P.dst_plane_stride) = make_uint2(pack4b(B[0], B[1], B[2], B[3]), pack4b(B[4], B[5], B[6], B[7]));
 						}
-						unsigned char *dp = (unsigned char *)P.dst + img * P.dst_img_stride + (long long)row * P.dst_pitch + cb;
-						*(uint2 *)dp = make_uint2(pack4b(R[0], R[1], R[2], R[3]), pack4b(R[4], R[5], R[6], R[7]));
-						*(uint2 *)(dp + P.dst_plane_stride) = make_uint2(pack4b(G[0], G[1], G[2], G[3]), pack4b(G[4], G[5], G[6], G[7]));
-						*(uint2 *)(dp + 2 * P.dst_plane_stride) = make_uint2(pack4b(B[0], B[1], B[2], B[3]), pack4b(B[4], B[5], B[6], B[7]));
 					}
 				}
 			}
