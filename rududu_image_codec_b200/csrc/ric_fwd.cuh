@@ -504,16 +504,22 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 		if (mark) io.rows[0].x = (io.rows[0].x & 0xFFFF0000u) | 0x8000u;
 		char *rowp = arena + b.off + ((long long)y0 * b.stride + x0) * 2;
 		const long long pitch = (long long)b.stride * 2;
-#pragma unroll
-		for (int r = 0; r < 4; r++) {
-			if (r >= bh) break;  // warp-uniform
-			const uint2 wv = io.rows[r];
-			if (bw == 4) *(uint2 *)(rowp + r * pitch) = wv;
-			else {
-				short *q = (short *)(rowp + r * pitch);
-				if (bw > 0) q[0] = (short)(wv.x & 0xFFFF);
-				if (bw > 1) q[1] = (short)(wv.x >> 16);
-				if (bw > 2) q[2] = (short)(wv.y & 0xFFFF);
+		if (bw == 4 && bh == 4) {  // the usual case: four 8-byte stores off one running pointer
+			*(uint2 *)rowp = io.rows[0]; rowp += pitch;
+			*(uint2 *)rowp = io.rows[1]; rowp += pitch;
+			*(uint2 *)rowp = io.rows[2]; rowp += pitch;
+			*(uint2 *)rowp = io.rows[3];
+		} else {
+#pragma unroll 1
+			for (int r = 0; r < bh; r++, rowp += pitch) {
+				const uint2 wv = r == 0 ? io.rows[0] : r == 1 ? io.rows[1] : r == 2 ? io.rows[2] : io.rows[3];
+				if (bw == 4) *(uint2 *)rowp = wv;
+				else {
+					short *q = (short *)rowp;
+					if (bw > 0) q[0] = (short)(wv.x & 0xFFFF);
+					if (bw > 1) q[1] = (short)(wv.x >> 16);
+					if (bw > 2) q[2] = (short)(wv.y & 0xFFFF);
+				}
 			}
 		}
 	}
