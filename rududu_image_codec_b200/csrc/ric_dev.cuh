@@ -20,6 +20,24 @@ constexpr int STRIP_W = 240;
 constexpr int LANE_W = 8;
 constexpr unsigned FULL = 0xffffffffu;
 
+// 8 bytes through the read-only path if `ok`, else zeros: one predicated LDG, never a branch
+__device__ __forceinline__ uint2 ldg_u2_if(const void *p, bool ok)
+{
+	uint2 v;
+	asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\t@q ld.global.nc.v2.u32 {%0, %1}, [%2];\n\t}"
+	    : "=&r"(v.x), "=&r"(v.y) : "l"(p), "r"((int)ok));
+	return v;
+}
+
+__device__ __forceinline__ uint4 ldg_u4_if(const void *p, bool ok)  // 16 bytes, likewise
+{
+	uint4 v;
+	asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.b32 %0, 0;\n\tmov.b32 %1, 0;\n\tmov.b32 %2, 0;\n\tmov.b32 %3, 0;\n\t"
+	    "@q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+	    : "=&r"(v.x), "=&r"(v.y), "=&r"(v.z), "=&r"(v.w) : "l"(p), "r"((int)ok));
+	return v;
+}
+
 template <bool SH>
 __device__ __forceinline__ int TR(int v) { return SH ? (int)(short)v : v; }
 

@@ -75,28 +75,22 @@ template <int SRC>
 __device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const void *base, long long row_off, int cb, bool ok,
                                          long long plane_stride, int plane)
 {
-#pragma unroll
-	for (int i = 0; i < RawRow<SRC>::N; i++) raw.r[i] = 0;
-	if (!ok) return;
-	if (SRC == SRC_U8_GRAY) {
-		uint2 a = __ldg((const uint2 *)((const unsigned char *)base + row_off + cb));
+	if constexpr (SRC == SRC_U8_GRAY) {  // the u8 sources: predicated loads, no branch in the row loop
+		const uint2 a = ldg_u2_if((const unsigned char *)base + row_off + cb, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y;
-	} else if (SRC == SRC_U8_RGB) {
+		return;
+	} else if constexpr (SRC == SRC_U8_RGB) {
 		const unsigned char *p = (const unsigned char *)base + row_off + cb;
-		uint2 a = __ldg((const uint2 *)p);
-		raw.r[0] = a.x; raw.r[1] = a.y;
-		if (plane != 0) {
-			uint2 g = __ldg((const uint2 *)(p + plane_stride));
-			raw.r[2] = g.x; raw.r[3] = g.y;
-		}
-		uint2 b = __ldg((const uint2 *)(p + 2 * plane_stride));
-		raw.r[4] = b.x; raw.r[5] = b.y;
-	} else if (SRC == SRC_S16) {
-		uint4 a = __ldg((const uint4 *)((const short *)base + row_off + cb));
+		const uint2 a = ldg_u2_if(p, ok), g = ldg_u2_if(p + plane_stride, ok && plane != 0), b = ldg_u2_if(p + 2 * plane_stride, ok);
+		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = g.x; raw.r[3] = g.y; raw.r[4] = b.x; raw.r[5] = b.y;
+		return;
+	}
+	if constexpr (SRC == SRC_S16) {
+		const uint4 a = ldg_u4_if((const short *)base + row_off + cb, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = a.z; raw.r[3] = a.w;
-	} else {
+	} else if constexpr (SRC == SRC_S32) {
 		const int *p = (const int *)base + row_off + cb;
-		uint4 a = __ldg((const uint4 *)p), b = __ldg((const uint4 *)(p + 4));
+		const uint4 a = ldg_u4_if(p, ok), b = ldg_u4_if(p + 4, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = a.z; raw.r[3] = a.w;
 		raw.r[4] = b.x; raw.r[5] = b.y; raw.r[6] = b.z; raw.r[7] = b.w;
 	}
@@ -504,6 +498,7 @@ __device__ __forceinline__ void flush_blocks_packed(const FwdParams &P, RingT &r
 		if (mark) io.rows[0].x = (io.rows[0].x & 0xFFFF0000u) | 0x8000u;
 		char *rowp = arena + b.off + ((long long)y0 * b.stride + x0) * 2;
 		const long long pitch = (long long)b.stride * 2;
+		// (predicated stores instead of these branches were measured 2.5 % slower: profiles/README.md, round 2)
 		if (bw == 4 && bh == 4) {  // the usual case: four 8-byte stores off one running pointer
 			*(uint2 *)rowp = io.rows[0]; rowp += pitch;
 			*(uint2 *)rowp = io.rows[1]; rowp += pitch;

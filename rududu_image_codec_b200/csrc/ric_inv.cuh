@@ -60,8 +60,8 @@ template <bool SH>
 __device__ __forceinline__ typename RawIn<SH>::vec ldvec(const char *rowp, int col, bool ok)
 {
 	typename RawIn<SH>::vec z;
-	if (SH) { uint2 t = make_uint2(0, 0); if (ok) t = __ldg((const uint2 *)(rowp + 2 * (long long)col)); *(uint2 *)&z = t; }
-	else { int4 t = make_int4(0, 0, 0, 0); if (ok) t = __ldg((const int4 *)(rowp + 4 * (long long)col)); *(int4 *)&z = t; }
+	if (SH) { const uint2 t = ldg_u2_if(rowp + 2 * (long long)col, ok); *(uint2 *)&z = t; }  // predicated, no branch
+	else { const uint4 t = ldg_u4_if(rowp + 4 * (long long)col, ok); *(uint4 *)&z = t; }
 	return z;
 }
 
@@ -127,8 +127,7 @@ __device__ __forceinline__ void load_in(RawIn<SH> &in, const InvParams &P, const
 		if (SH) { const uint2 a = *(const uint2 *)&r; in.l.x = (int)a.x; in.l.y = (int)a.y; }
 		else in.l = *(const int4 *)&r;
 	} else if (P.llsrc == LLSRC_S16) {
-		uint2 a = make_uint2(0, 0);
-		if (l_ok) a = __ldg((const uint2 *)(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 2));
+		const uint2 a = ldg_u2_if(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 2, l_ok);
 		in.l.x = (int)a.x; in.l.y = (int)a.y;
 	} else {
 		if (l_ok) in.l = __ldg((const int4 *)(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 4));
