@@ -107,8 +107,8 @@ __device__ __forceinline__ int dp4a_pick(unsigned word, int mult, int k, int c)
 
 
 // Per-plane constants of the RGB closed forms below, one row per plane in shared memory (filled once per CTA):
-// the byte-position-shifted multipliers of R, B and G, then {c, m1, m2, down-shift for q == 0}.  Read back with
-// four 128-bit loads per row pair: kept in registers across the loop they would cost 16 registers, recomputed
+// the byte-position-shifted multipliers of R, B and G, then {c, m, down-shift for q == 0, unused}.  Read back with
+// four 128-bit loads per row pair: kept in registers across the loop they would cost 15 registers, recomputed
 // from `plane` they cost 2 instructions per sample (both measured).
 struct ColourTab { int4 aR, aB, aG, cm; };
 
@@ -119,8 +119,8 @@ __device__ __forceinline__ void colour_tab_fill(ColourTab *tab, int shift)  // t
 		const int aR = plane == 0 ? 8 : plane == 1 ? -4 : 4, aB = plane == 0 ? -8 : plane == 1 ? -4 : 4, aG = plane == 0 ? 0 : 8;
 		int v;
 		if (j < 12) v = (int)((unsigned)((j < 4 ? aR : j < 8 ? aB : aG) & 0xFF) << (8 * (j & 3)));
-		else v = j == 12 ? (plane == 0 ? 0 : plane == 1 ? 7 : -2048) : j == 13 ? (plane == 1 ? ~7 : ~0) : j == 14 ? (plane == 2 ? ~15 : ~0)
-		                 : (shift ? 0 : plane == 2 ? 4 : 3);
+		else v = j == 12 ? (plane == 0 ? 0 : plane == 1 ? 4 : -2048) : j == 13 ? (plane == 0 ? ~0 : plane == 1 ? ~7 : ~15)
+		                 : j == 14 ? (shift ? 0 : plane == 2 ? 4 : 3) : 0;
 		((int *)tab)[i] = v;
 	}
 }
@@ -142,15 +142,15 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)  // IDP.4A.U8.S
 // RGBtoYCoCg<shift> (ric.cpp:76-91; planes 0 Co, 1 Cg, 2 Y) of two rows of 8 pixels.  The reference's lifting chain
 // Co = R - B, t = B + (Co >> 1), Cg = G - t, Y = t + (Cg >> 1) - 128, then << 3 (chroma) / << 4 (luma), has closed
 // forms, because floors of integers nest (t = (R + B) >> 1, Y + 128 = (R + 2G + B) >> 2):
-//   Co << 3 = 8R - 8B
-//   Cg << 3 = 8G + ((7 - 4R - 4B) & ~7)        (-(n & ~7) = (7 - n) & ~7 for n = 4(R + B))
+//   Co << 3 =  8R - 8B
+//   Cg << 3 = (8G - 4R - 4B + 4) & ~7        (8G - 4(R + B) is 8 Cg or 8 Cg - 4)
 //   Y  << 4 = (4R + 8G + 4B - 2048) & ~15
 // (checked over all 2^24 pixels in tests/test_host_logic.py).  Each is a dot product of pixel bytes with small
-// constants plus masks: IDP.4A picks the byte, scales it and accumulates in ONE FMA-pipe instruction -- no byte
-// extraction and no shifts on the ALU pipe.  One sequence, ((aR*R + aB*B + c) & m1) + aG*G) & m2, serves the three
-// planes with the warp's constants from `tab`: no per-plane branches, small code (the kernel is
-// instruction-fetch sensitive: profiles/README.md, round 2).  q == 0 (no up-shift): the values are exact multiples
-// and are shifted back down.
+// constants plus one mask: IDP.4A picks the byte, scales it and accumulates in ONE FMA-pipe instruction -- no byte
+// extraction and no shifts on the ALU pipe.  One sequence, (aR*R + aB*B + aG*G + c) & m, serves the three planes
+// with the warp's constants from `tab`: no per-plane branches, small code (the kernel is instruction-fetch
+// sensitive: profiles/README.md, round 2).  q == 0 (no up-shift): the values are exact multiples and are shifted
+// back down.
 __device__ __forceinline__ void convert_rgb2(const RawRow<SRC_U8_RGB> &rawE, const RawRow<SRC_U8_RGB> &rawO, int (&ve)[8], int (&vo)[8],
                                              const ColourTab *tab)
 {
@@ -160,12 +160,12 @@ __device__ __forceinline__ void convert_rgb2(const RawRow<SRC_U8_RGB> &rawE, con
 		const int j = k & 3;
 		const int sR = j == 0 ? aR.x : j == 1 ? aR.y : j == 2 ? aR.z : aR.w, sB = j == 0 ? aB.x : j == 1 ? aB.y : j == 2 ? aB.z : aB.w;
 		const int sG = j == 0 ? aG.x : j == 1 ? aG.y : j == 2 ? aG.z : aG.w;
-		ve[k] = dp4a_us(rawE.r[2 + (k >> 2)], sG, dp4a_us(rawE.r[k >> 2], sR, dp4a_us(rawE.r[4 + (k >> 2)], sB, cm.x)) & cm.y) & cm.z;
-		vo[k] = dp4a_us(rawO.r[2 + (k >> 2)], sG, dp4a_us(rawO.r[k >> 2], sR, dp4a_us(rawO.r[4 + (k >> 2)], sB, cm.x)) & cm.y) & cm.z;
+		ve[k] = dp4a_us(rawE.r[2 + (k >> 2)], sG, dp4a_us(rawE.r[k >> 2], sR, dp4a_us(rawE.r[4 + (k >> 2)], sB, cm.x))) & cm.y;
+		vo[k] = dp4a_us(rawO.r[2 + (k >> 2)], sG, dp4a_us(rawO.r[k >> 2], sR, dp4a_us(rawO.r[4 + (k >> 2)], sB, cm.x))) & cm.y;
 	}
-	if (cm.w) {  // warp-uniform, rare
+	if (cm.z) {  // warp-uniform, rare
 #pragma unroll
-		for (int k = 0; k < 8; k++) { ve[k] >>= cm.w; vo[k] >>= cm.w; }
+		for (int k = 0; k < 8; k++) { ve[k] >>= cm.z; vo[k] >>= cm.z; }
 	}
 }
 

@@ -12,6 +12,5 @@ def test_colour_closed_forms_equal_the_lifting_chain():
     cg = g - t
     y = t + (cg >> 1) - 128
     assert np.array_equal(co << 3, 8 * r - 8 * b + 0 * g)
-    m = (-4 * r - 4 * b + 7) & ~7
-    assert np.array_equal(cg << 3, 8 * g + m)
+    assert np.array_equal(cg << 3, (8 * g - 4 * r - 4 * b + 4) & ~7)
     assert np.array_equal(y << 4, (4 * r + 8 * g + 4 * b - 2048) & ~15)
