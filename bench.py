@@ -417,13 +417,17 @@ def copy_only_roof(torch, dev, pairs, steps, max_over_ranks):
                 dst.copy_(src, non_blocking=True)
     go()
     torch.cuda.synchronize()
-    if torch.distributed.is_initialized():
-        torch.distributed.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        go()
-    torch.cuda.synchronize()
-    return max_over_ranks(time.perf_counter() - t0, dev)
+    best = None
+    for _ in range(2):  # a roof: the faster of two passes (the link's throughput wanders by several per cent)
+        if torch.distributed.is_initialized():
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            go()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, dev)
+        best = dt if best is None else min(best, dt)
+    return best
 
 
 def class_api_figure(capi, dev_index, q, with_reference):
