@@ -88,12 +88,29 @@ struct ric_ctx {
 	int ev_n[2];
 	int target_warps;
 	int use_tma;
+	int use_pdl;            // programmatic dependent launch between the level kernels of one call (RIC_PDL, default 1)
 	int use_inv0;
 	int use_fwd0;                        // packed level-0 forward kernel, experimental (RIC_FWD0=1)
 };
 
 // ---------------------------------------------------------------------------------------------
 // kernel dispatch tables
+
+// Level kernels of one call are launched back to back on one stream; with programmatic dependent launch the next
+// level's CTAs become resident while the previous level drains and wait in griddepcontrol.wait (top of the kernels)
+// until its memory is visible: the launch latency and the kernel preamble leave the critical path of a single image.
+template <class P>
+static cudaError_t launch_level(void (*fn)(const P), unsigned grid, unsigned block, cudaStream_t st, const P &params, bool pdl)
+{
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, fn, params);
+}
 
 typedef void (*fwd_fn)(const FwdParams);
 typedef void (*inv_fn)(const InvParams);
@@ -380,6 +397,7 @@ int ric_create(ric_ctx **out, int device, int width, int height, int channels, i
 	// 16: profiles/README.md), so it is opt-in
 	c->use_fwd0 = getenv("RIC_FWD0", 0);
 	c->use_inv0 = getenv("RIC_INV0", 0);  // packed finest inverse level (ric_inv0.cuh)
+	c->use_pdl = getenv("RIC_PDL", 1);  // programmatic dependent launch between the level kernels of a call
 	c->use_tma = getenv("RIC_TMA", 0);  // gray level 0 of the packed kernel through the TMA unit (experiment, profiles/README.md)
 #define CKD(call)                                                                    \
 	do {                                                                             \
@@ -605,7 +623,7 @@ static int launch_forward(ric_ctx *c, const void *d_src, int src_kind, long long
 			if (njobs >= (1ll << 31)) return set_err(RIC_E_ARG, "forward: batch too large for one launch");
 			const int wpb = fwd_warps(sh);
 			const unsigned grid = (unsigned)std::min<long long>((njobs + wpb - 1) / wpb, (long long)c->sm_count * 4);
-			fn<<<grid, wpb * 32, 0, st>>>(P);
+			CK(launch_level(fn, grid, wpb * 32, st, P, c->use_pdl && !c->profiling && lv > 0));
 		}
 		CK(cudaGetLastError());
 		c->launches++;
@@ -686,10 +704,10 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 			}
 		} else if (dst == DST_U8_RGB) {
 			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * (6 / INV_RGB_GROUPS));
-			fn<<<grid, INV_RGB_GROUPS * 96, 0, st>>>(P);
+			CK(launch_level(fn, grid, INV_RGB_GROUPS * 96, st, P, c->use_pdl && !c->profiling && lv < g.nlev - 1));
 		} else {
 			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_WARPS - 1) / INV_WARPS, (long long)c->sm_count * 4);
-			fn<<<grid, INV_WARPS * 32, 0, st>>>(P);
+			CK(launch_level(fn, grid, INV_WARPS * 32, st, P, c->use_pdl && !c->profiling && lv < g.nlev - 1));
 		}
 		CK(cudaGetLastError());
 		c->launches++;

@@ -662,6 +662,10 @@ __global__ void __launch_bounds__(fwd_warps(SH) * 32, 4) fwd_level_kernel(const 
 	__shared__ ColourTab s_ctab[SRC == SRC_U8_RGB ? 3 : 1];
 	for (int i = threadIdx.x; i < (int)(sizeof(s_qb) / 4); i += blockDim.x) ((int *)s_qb)[i] = ((const int *)P.qb)[i];
 	if (SRC == SRC_U8_RGB) colour_tab_fill(s_ctab, P.shift);
+	// programmatic dependent launch (ric_b200.cu launch_level): let the next level's CTAs become resident as this
+	// grid drains, and do not touch what the previous level wrote before it is complete and visible
+	asm volatile("griddepcontrol.launch_dependents;");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const long long njobs = (long long)P.nstrips * P.nplanes * P.nsegs * P.nimages;

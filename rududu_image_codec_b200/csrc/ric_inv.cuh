@@ -355,6 +355,8 @@ __global__ void __launch_bounds__(DST == DST_U8_RGB ? INV_RGB_GROUPS * 96 : INV_
 	RgbStage *s_stage = (RgbStage *)s_stage_raw;
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int grp = RGB ? wib / 3 : 0, wig = RGB ? wib % 3 : 0;
+	asm volatile("griddepcontrol.launch_dependents;");  // programmatic dependent launch, see fwd_level_kernel
+	asm volatile("griddepcontrol.wait;" ::: "memory");
 	const long long njobs = (long long)P.nstrips * (RGB ? 1 : P.nplanes) * P.nsegs * P.nimages;
 	for (;;) {
 		unsigned long long job = 0;
