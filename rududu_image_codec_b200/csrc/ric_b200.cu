@@ -703,7 +703,7 @@ static int launch_inverse(ric_ctx *c, const char *d_arena, int n, int nplanes, i
 				inv0_kernel<DST_U8_GRAY><<<grid, INV_WARPS * 32, 0, st>>>(P);
 			}
 		} else if (dst == DST_U8_RGB) {
-			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * (6 / INV_RGB_GROUPS));
+			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_RGB_GROUPS - 1) / INV_RGB_GROUPS, (long long)c->sm_count * getenv("RIC_INV_RGB_OCC", 6 / INV_RGB_GROUPS));
 			CK(launch_level(fn, grid, INV_RGB_GROUPS * 96, st, P, c->use_pdl && !c->profiling && lv < g.nlev - 1));
 		} else {
 			const unsigned grid = (unsigned)std::min<long long>((njobs + INV_WARPS - 1) / INV_WARPS, (long long)c->sm_count * 4);

@@ -107,31 +107,65 @@ __device__ __forceinline__ void unpack4(const typename RawIn<SH>::vec &r, int (&
 	}
 }
 
+// Running row pointers of one job's band loads: element (row, bc) of D / H (row t), V / LL (row t - 1), advanced by
+// one row per load_in call (the calls of a job come with t, t + 1, t + 2, ...), so the row loop carries four
+// 64-bit adds instead of four 64-bit multiplies and their address chains.
+struct InPtrs { const char *d, *h, *v, *l; long long sd, sh, sv, sl; };
+
 template <bool SH>
-__device__ __forceinline__ void load_in(RawIn<SH> &in, const InvParams &P, const char *arena, const char *llp, int t,
-                                        int bc, bool col_ok)
+__device__ __forceinline__ InPtrs in_ptrs(const InvParams &P, const char *arena, const char *llp, int t, int bc)
+{
+	constexpr int ES = SH ? 2 : 4;
+	const BandRef &D = P.band[0], &H = P.band[1], &V = P.band[2];
+	InPtrs p;
+	p.sd = (long long)D.stride * ES; p.sh = (long long)H.stride * ES; p.sv = (long long)V.stride * ES;
+	p.d = arena + D.off + t * p.sd + (long long)bc * ES;
+	p.h = arena + H.off + t * p.sh + (long long)bc * ES;
+	p.v = arena + V.off + (t - 1) * p.sv + (long long)bc * ES;
+	if (P.llsrc == LLSRC_BAND) { p.sl = (long long)P.lband.stride * ES; p.l = arena + P.lband.off + (t - 1) * p.sl + (long long)bc * ES; }
+	else {
+		const int es = P.llsrc == LLSRC_S16 ? 2 : 4;
+		p.sl = (long long)P.ll_pitch * es; p.l = llp + (t - 1) * p.sl + (long long)bc * es;
+	}
+	return p;
+}
+
+template <bool SH>
+__device__ __forceinline__ typename RawIn<SH>::vec ldvec_at(const char *p, bool ok)
+{
+	typename RawIn<SH>::vec z;
+	if (SH) { const uint2 t = ldg_u2_if(p, ok); *(uint2 *)&z = t; }  // predicated, no branch
+	else { const uint4 t = ldg_u4_if(p, ok); *(uint4 *)&z = t; }
+	return z;
+}
+
+template <bool SH, int TRANS>
+__device__ __forceinline__ void load_in(RawIn<SH> &in, const InvParams &P, const char *arena, InPtrs &p, int t, int bc, bool col_ok)
 {
 	constexpr int ES = SH ? 2 : 4;
 	const int h = P.h;
 	const bool e_ok = col_ok && 2 * t < h;
 	const bool o_ok = col_ok && t >= 1 && 2 * t - 1 < h;
 	const BandRef &D = P.band[0], &H = P.band[1], &V = P.band[2];
-	in.d = ldvec<SH>(arena + D.off + (long long)t * D.stride * ES, bc, e_ok && bc < D.dimx);
-	const long long hoff = t == 1 ? (long long)P.h_row1_off : (long long)t * H.stride;
-	in.h = ldvec<SH>(arena + H.off + hoff * ES, bc, e_ok && bc < H.dimx);
-	in.v = ldvec<SH>(arena + V.off + (long long)(t - 1) * V.stride * ES, bc, o_ok && bc < V.dimx);
+	in.d = ldvec_at<SH>(p.d, e_ok && bc < D.dimx);
+	const char *hp = p.h;
+	if (TRANS == T53 && t == 1) hp = arena + H.off + ((long long)P.h_row1_off + bc) * ES;  // the reference's stride slip, SURVEY Q1
+	in.h = ldvec_at<SH>(hp, e_ok && bc < H.dimx);
+	in.v = ldvec_at<SH>(p.v, o_ok && bc < V.dimx);
 	in.l = make_int4(0, 0, 0, 0);
 	const bool l_ok = o_ok && bc < (P.w >> 1);
 	if (P.llsrc == LLSRC_BAND) {
-		typename RawIn<SH>::vec r = ldvec<SH>(arena + P.lband.off + (long long)(t - 1) * P.lband.stride * ES, bc, l_ok);
+		typename RawIn<SH>::vec r = ldvec_at<SH>(p.l, l_ok);
 		if (SH) { const uint2 a = *(const uint2 *)&r; in.l.x = (int)a.x; in.l.y = (int)a.y; }
 		else in.l = *(const int4 *)&r;
 	} else if (P.llsrc == LLSRC_S16) {
-		const uint2 a = ldg_u2_if(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 2, l_ok);
+		const uint2 a = ldg_u2_if(p.l, l_ok);
 		in.l.x = (int)a.x; in.l.y = (int)a.y;
 	} else {
-		if (l_ok) in.l = __ldg((const int4 *)(llp + ((long long)(t - 1) * P.ll_pitch + bc) * 4));
+		const uint4 a = ldg_u4_if(p.l, l_ok);
+		in.l = make_int4((int)a.x, (int)a.y, (int)a.z, (int)a.w);
 	}
+	p.d += p.sd; p.h += p.sh; p.v += p.sv; p.l += p.sl;
 }
 
 // unpack + dequantise (TSUQi: pBand[n] *= Quant, truncating store) into interleaved even/odd rows.
@@ -210,13 +244,14 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 	const int qd = P.dq[plane][0], qh = P.dq[plane][1], qv = P.dq[plane][2];
 	const int ql = P.llsrc == LLSRC_BAND ? P.dq[plane][3] : 1;
 	RawIn<SH> in;
-	load_in<SH>(in, P, arena, llp, t_begin, bc, col_ok);
+	InPtrs ip = in_ptrs<SH>(P, arena, llp, t_begin, bc);
+	load_in<SH, TRANS>(in, P, arena, ip, t_begin, bc, col_ok);
 
 #pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
 		int xe[8], xo[8];
 		unpack_in<SH, TRANS>(in, P, qd, qh, qv, ql, xe, xo);
-		load_in<SH>(in, P, arena, llp, t + 1, bc, col_ok);  // prefetch
+		load_in<SH, TRANS>(in, P, arena, ip, t + 1, bc, col_ok);  // prefetch
 
 		const int r4 = 2 * t - 1, r3 = 2 * t - 2, r2 = 2 * t - 3, r1 = 2 * t - 4;
 		const bool edge_y = (r1 - 1 <= 0) || (2 * t >= h - 1);

@@ -203,7 +203,8 @@ __device__ __forceinline__ void inv0_job(const InvParams &P, long long job, RgbS
 
 	const int t_begin = max((y0 >> 1) - 2, 0), t_last = (y1 + 3) >> 1;
 	RawIn<true> in;
-	load_in<true>(in, P, arena, llp, t_begin, bc, col_ok);
+	InPtrs ip = in_ptrs<true>(P, arena, llp, t_begin, bc);
+	load_in<true, T97>(in, P, arena, ip, t_begin, bc, col_ok);
 
 #pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
@@ -218,7 +219,7 @@ __device__ __forceinline__ void inv0_job(const InvParams &P, long long job, RgbS
 		const bool in_ok = max((int)(short)(mx & 0xFFFF), (int)mx >> 16) <= clim && min((int)(short)(mn & 0xFFFF), (int)mn >> 16) >= -clim;
 		const uint2 cd = in.d, chh = in.h, cv = in.v;
 		const int2 cl = make_int2(in.l.x, in.l.y);
-		load_in<true>(in, P, arena, llp, t + 1, bc, col_ok);  // prefetch
+		load_in<true, T97>(in, P, arena, ip, t + 1, bc, col_ok);  // prefetch
 
 		const int r1 = 2 * t - 4;
 		const bool interior = !((r1 - 1 <= 0) || (2 * t >= h - 1));
