@@ -72,25 +72,21 @@ struct RawRow {
 // issue the global loads of one row (8 columns starting at cb) -- conversion happens later.
 // RGB: plane 0 (Co) does not need G.
 template <int SRC>
-__device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const void *base, long long row_off, int cb, bool ok,
-                                         long long plane_stride, int plane)
+__device__ __forceinline__ void load_raw(RawRow<SRC> &raw, const char *p, bool ok, long long plane_stride, int plane)
 {
-	if constexpr (SRC == SRC_U8_GRAY) {  // the u8 sources: predicated loads, no branch in the row loop
-		const uint2 a = ldg_u2_if((const unsigned char *)base + row_off + cb, ok);
+	// p: address of this lane's first sample of the row (the row loop advances it by two rows per iteration: no
+	// per-load 64-bit multiply).  Predicated loads, no branch.
+	if constexpr (SRC == SRC_U8_GRAY) {
+		const uint2 a = ldg_u2_if(p, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y;
-		return;
 	} else if constexpr (SRC == SRC_U8_RGB) {
-		const unsigned char *p = (const unsigned char *)base + row_off + cb;
 		const uint2 a = ldg_u2_if(p, ok), g = ldg_u2_if(p + plane_stride, ok && plane != 0), b = ldg_u2_if(p + 2 * plane_stride, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = g.x; raw.r[3] = g.y; raw.r[4] = b.x; raw.r[5] = b.y;
-		return;
-	}
-	if constexpr (SRC == SRC_S16) {
-		const uint4 a = ldg_u4_if((const short *)base + row_off + cb, ok);
+	} else if constexpr (SRC == SRC_S16) {
+		const uint4 a = ldg_u4_if(p, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = a.z; raw.r[3] = a.w;
-	} else if constexpr (SRC == SRC_S32) {
-		const int *p = (const int *)base + row_off + cb;
-		const uint4 a = ldg_u4_if(p, ok), b = ldg_u4_if(p + 4, ok);
+	} else {
+		const uint4 a = ldg_u4_if(p, ok), b = ldg_u4_if(p + 16, ok);
 		raw.r[0] = a.x; raw.r[1] = a.y; raw.r[2] = a.z; raw.r[3] = a.w;
 		raw.r[4] = b.x; raw.r[5] = b.y; raw.r[6] = b.z; raw.r[7] = b.w;
 	}
@@ -572,10 +568,13 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<S
 
 	const int t_begin = (y0 >> 1) - 2, t_last = (y1r >> 1) + 1;
 	RawRow<SRC> rawE, rawO;
+	constexpr int SES = (SRC == SRC_U8_GRAY || SRC == SRC_U8_RGB) ? 1 : SRC == SRC_S16 ? 2 : 4;  // bytes per source sample
+	const long long rowstep = (long long)P.src_pitch * SES;
+	const char *prow = (const char *)src + (long long)(2 * t_begin) * rowstep + (long long)cb * SES;  // row 2t, this lane's columns
 	{
 		const int re = 2 * t_begin, ro = re + 1;
-		load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
-		load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
+		load_raw<SRC>(rawE, prow, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
+		load_raw<SRC>(rawO, prow + rowstep, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 	}
 
 	// Two source rows per iteration: their conversions and horizontal passes are independent
@@ -587,8 +586,9 @@ __device__ __forceinline__ void fwd_job(const FwdParams &P, unsigned job, Ring<S
 		else { convert_raw<SRC>(rawE, ne, plane, P.shift); convert_raw<SRC>(rawO, no, plane, P.shift); }
 		{  // prefetch the next row pair
 			const int re = 2 * t + 2, ro = re + 1;
-			load_raw<SRC>(rawE, src, (long long)re * P.src_pitch, cb, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
-			load_raw<SRC>(rawO, src, (long long)ro * P.src_pitch, cb, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
+			prow += 2 * rowstep;
+			load_raw<SRC>(rawE, prow, col_ok && re >= 0 && re < h, P.src_plane_stride, plane);
+			load_raw<SRC>(rawO, prow + rowstep, col_ok && ro >= 0 && ro < h, P.src_plane_stride, plane);
 		}
 		if (ex.on) { row_fwd<SH, TRANS, NT, true>(ne, ex); row_fwd<SH, TRANS, NT, true>(no, ex); }
 		else { row_fwd<SH, TRANS, NT, false>(ne, ex); row_fwd<SH, TRANS, NT, false>(no, ex); }
