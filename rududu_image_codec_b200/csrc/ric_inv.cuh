@@ -72,6 +72,13 @@ __device__ __forceinline__ typename RawIn<SH>::vec ldvec(const char *rowp, int c
 __device__ __forceinline__ int s16_lo_fma(unsigned w) { int d; asm("dp2a.lo.s32.u32 %0, %1, 0x0001, 0;" : "=r"(d) : "r"(w)); return d; }
 __device__ __forceinline__ int s16_hi_fma(unsigned w) { int d; asm("dp2a.lo.s32.u32 %0, %1, 0x0100, 0;" : "=r"(d) : "r"(w)); return d; }
 
+// c + a.s16[0] * b.u8[0] + a.s16[1] * b.u8[1], one FMA-pipe instruction (IDP.2A.LO.S16.U8)
+__device__ __forceinline__ int dp2a_lo_u(unsigned a, int b, int c)
+{
+	int d;
+	asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
 // sign-extended half `hi` of a packed pair plus a constant, one FMA-pipe instruction
 __device__ __forceinline__ int s16_plus(unsigned w, int hi, int c)
 {
@@ -173,10 +180,21 @@ __device__ __forceinline__ void load_in(RawIn<SH> &in, const InvParams &P, const
 // (the (C)(l + r) temporary of U4, the C-typed result of U4 / U3, or iU4_last which truncates its
 // operand) -- 5/3 and Haar feed them straight into a shift and truncate here.
 template <bool SH, int TRANS>
-__device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &P, int qd, int qh, int qv, int ql,
+__device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &P, int qd, int qh, int qv, int ql, bool smallq,
                                           int (&xe)[8], int (&xo)[8])
 {
 	constexpr bool S = SH && TRANS != T97;
+	if (SH && TRANS == T97 && smallq) {
+		// every multiplier fits a byte (fine quantisers -- the common case -- and q == 0): IDP.2A sign-extends one half
+		// of a packed pair AND multiplies it, one FMA-pipe instruction per sample instead of unpack + IMAD
+		const uint2 D = *(const uint2 *)&in.d, H = *(const uint2 *)&in.h, V = *(const uint2 *)&in.v;
+		const unsigned L0 = (unsigned)in.l.x, L1 = (unsigned)in.l.y;
+		xe[0] = dp2a_lo_u(D.x, qd, 0); xe[2] = dp2a_lo_u(D.x, qd << 8, 0); xe[4] = dp2a_lo_u(D.y, qd, 0); xe[6] = dp2a_lo_u(D.y, qd << 8, 0);
+		xe[1] = dp2a_lo_u(H.x, qh, 0); xe[3] = dp2a_lo_u(H.x, qh << 8, 0); xe[5] = dp2a_lo_u(H.y, qh, 0); xe[7] = dp2a_lo_u(H.y, qh << 8, 0);
+		xo[0] = dp2a_lo_u(V.x, qv, 0); xo[2] = dp2a_lo_u(V.x, qv << 8, 0); xo[4] = dp2a_lo_u(V.y, qv, 0); xo[6] = dp2a_lo_u(V.y, qv << 8, 0);
+		xo[1] = dp2a_lo_u(L0, ql, 0); xo[3] = dp2a_lo_u(L0, ql << 8, 0); xo[5] = dp2a_lo_u(L1, ql, 0); xo[7] = dp2a_lo_u(L1, ql << 8, 0);
+		return;
+	}
 	int d[4], hh[4], v[4], l[4];
 	unpack4<SH>(in.d, d);
 	unpack4<SH>(in.h, hh);
@@ -243,14 +261,18 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 	const int t_begin = max((y0 >> 1) - 2, 0), t_last = (y1 + 3) >> 1;
 	const int qd = P.dq[plane][0], qh = P.dq[plane][1], qv = P.dq[plane][2];
 	const int ql = P.llsrc == LLSRC_BAND ? P.dq[plane][3] : 1;
+	// all four multipliers in 1..255 and the LL input a packed short plane: the one-instruction dequantiser of unpack_in
+	const bool smallq = SH && P.llsrc != LLSRC_S32 && (unsigned)(qd - 1) < 255u && (unsigned)(qh - 1) < 255u && (unsigned)(qv - 1) < 255u &&
+	                    (unsigned)(ql - 1) < 255u;
 	RawIn<SH> in;
 	InPtrs ip = in_ptrs<SH>(P, arena, llp, t_begin, bc);
 	load_in<SH, TRANS>(in, P, arena, ip, t_begin, bc, col_ok);
 
+	int slot_c = 0, set_c = 0;
 #pragma unroll 1
 	for (int t = t_begin; t <= t_last; t++) {
 		int xe[8], xo[8];
-		unpack_in<SH, TRANS>(in, P, qd, qh, qv, ql, xe, xo);
+		unpack_in<SH, TRANS>(in, P, qd, qh, qv, ql, smallq, xe, xo);
 		load_in<SH, TRANS>(in, P, arena, ip, t + 1, bc, col_ok);  // prefetch
 
 		const int r4 = 2 * t - 1, r3 = 2 * t - 2, r2 = 2 * t - 3, r1 = 2 * t - 4;
@@ -268,8 +290,7 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 		}
 		// finished: even row r1 (se3), odd row r2 (so4); both rows' horizontal passes are unrolled so
 		// that their dependency chains interleave (this kernel fits the instruction cache either way)
-		const int slot = RGB ? (t - t_begin) % 3 : 0;
-		const int set = RGB ? ((t - t_begin) / 3) & 1 : 0;
+		const int slot = RGB ? slot_c : 0, set = RGB ? set_c : 0;  // (t - t_begin) % 3 and ((t - t_begin) / 3) & 1, kept as counters
 #pragma unroll
 		for (int half = 0; half < 2; half++) {
 			int o[8];
@@ -374,6 +395,7 @@ __device__ __forceinline__ void inv_job(const InvParams &P, long long job, RgbSt
 					}
 				}
 			}
+			if (++slot_c == 3) { slot_c = 0; set_c ^= 1; }
 		}
 	}
 }
