@@ -65,9 +65,6 @@ __device__ __forceinline__ typename RawIn<SH>::vec ldvec(const char *rowp, int c
 	return z;
 }
 
-#ifndef RIC_EXP_UNPACK_DP2A
-#define RIC_EXP_UNPACK_DP2A 1
-#endif
 // halves of a packed pair, sign-extended on the FMA pipe (IDP.2A.LO.S16.U8 with the byte pairs (1, 0) / (0, 1))
 __device__ __forceinline__ int s16_lo_fma(unsigned w) { int d; asm("dp2a.lo.s32.u32 %0, %1, 0x0001, 0;" : "=r"(d) : "r"(w)); return d; }
 __device__ __forceinline__ int s16_hi_fma(unsigned w) { int d; asm("dp2a.lo.s32.u32 %0, %1, 0x0100, 0;" : "=r"(d) : "r"(w)); return d; }
@@ -101,13 +98,8 @@ __device__ __forceinline__ void unpack4(const typename RawIn<SH>::vec &r, int (&
 {
 	if (SH) {
 		const uint2 a = *(const uint2 *)&r;
-#if RIC_EXP_UNPACK_DP2A
 		o[0] = s16_lo_fma(a.x); o[1] = s16_hi_fma(a.x);
 		o[2] = s16_lo_fma(a.y); o[3] = s16_hi_fma(a.y);
-#else
-		o[0] = (int)(short)(a.x & 0xFFFF); o[1] = (int)a.x >> 16;
-		o[2] = (int)(short)(a.y & 0xFFFF); o[3] = (int)a.y >> 16;
-#endif
 	} else {
 		const int4 a = *(const int4 *)&r;
 		o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
@@ -202,13 +194,8 @@ __device__ __forceinline__ void unpack_in(const RawIn<SH> &in, const InvParams &
 	if (P.llsrc == LLSRC_S32 || (!SH && P.llsrc == LLSRC_BAND)) {
 		l[0] = in.l.x; l[1] = in.l.y; l[2] = in.l.z; l[3] = in.l.w;
 	} else {
-#if RIC_EXP_UNPACK_DP2A
 		l[0] = s16_lo_fma((unsigned)in.l.x); l[1] = s16_hi_fma((unsigned)in.l.x);
 		l[2] = s16_lo_fma((unsigned)in.l.y); l[3] = s16_hi_fma((unsigned)in.l.y);
-#else
-		l[0] = (int)(short)(in.l.x & 0xFFFF); l[1] = in.l.x >> 16;
-		l[2] = (int)(short)(in.l.y & 0xFFFF); l[3] = in.l.y >> 16;
-#endif
 	}
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
