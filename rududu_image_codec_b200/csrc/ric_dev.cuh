@@ -85,7 +85,7 @@ __device__ __forceinline__ int fS1(int x, int l, int r)
 {
 	if (TRANS == T97) { int t = TR<SH>(l + r); return TR<SH>(x - (t + (t >> 1))); }
 	if (TRANS == THAAR) return TR<SH>(x - r);  // i[0] -= i[1], wavelet2d.cpp:772
-	return TR<SH>(x - ((l + r) >> 1));
+	return TR<SH>(x + ((1 - l - r) >> 1));  // x - ((l + r) >> 1), same identity
 }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int fS1_first(int x, int r) { return TRANS == T97 ? TR<SH>(x - 3 * r) : TR<SH>(x - r); }
@@ -95,7 +95,9 @@ __device__ __forceinline__ int fS1_last(int x, int l) { return TRANS == T97 ? TR
 template <bool SH, int TRANS>
 __device__ __forceinline__ int fS2(int x, int l, int r)
 {
-	if (TRANS == T97) return TR<SH>(x - ((l + r) >> 4));
+	// x - ((l + r) >> 4), written as x + ((15 - l - r) >> 4): -floor(s / 16) = floor((15 - s) / 16) for every integer s,
+	// and this form is two instructions (a three-input add and a fused shift-add) instead of three
+	if (TRANS == T97) return TR<SH>(x + ((15 - l - r) >> 4));
 	if (TRANS == THAAR) return TR<SH>(x + (l >> 1));  // i[1] += i[0] >> 1, wavelet2d.cpp:773
 	return TR<SH>(x + ((l + r) >> 2));
 }
@@ -148,7 +150,7 @@ __device__ __forceinline__ int iU2(int x, int l, int r)
 {
 	if (TRANS == T97) return x + ((l + r) >> 4);
 	if (TRANS == THAAR) return TRI<SH>(x - (l >> 1));  // i[1] -= i[0] >> 1, wavelet2d.cpp:784
-	return TRI<SH>(x - ((l + r) >> 2));  // 5/3: feeds the un-truncated (l + r) >> 1 of U1
+	return TRI<SH>(x + ((3 - l - r) >> 2));  // 5/3: x - ((l + r) >> 2) (same identity); feeds the un-truncated (l + r) >> 1 of U1
 }
 template <bool SH, int TRANS>
 __device__ __forceinline__ int iU2_last(int x, int l) { return TRANS == T97 ? TRI<SH>(x + (l >> 3)) : TRI<SH>(x - (l >> 1)); }

@@ -44,3 +44,11 @@ def test_dequantiser_byte_multiplier_identity():
     for q in (1, 2, 96, 255):
         assert np.array_equal(lo * q + hi * 0, lo * q) and np.array_equal(lo * 0 + hi * q, hi * q)
         assert np.abs(lo * q).max() < 2 ** 31
+
+
+def test_negated_floor_shift_identity():
+    """ric_dev.cuh writes x - ((l + r) >> k) as x + ((2^k - 1 - l - r) >> k): one instruction less, same integer."""
+    import numpy as np
+    s = np.arange(-70000, 70000, dtype=np.int64)
+    for k in (1, 2, 4):
+        assert np.array_equal(-(s >> k), ((1 << k) - 1 - s) >> k)
