@@ -596,8 +596,48 @@ def run_ours(args):
         duplex_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_val = 2.0 * pixels_per_step * args.e2e_steps / max_over_ranks(e2e_s, dev) / 1e6
-    ctx_d.close()
+    e2e_single_val = 2.0 * pixels_per_step * args.e2e_steps / max_over_ranks(e2e_s, dev) / 1e6
+    # Throughput form of the same calls: consecutive steps alternate between two context pairs (one call in flight per
+    # context is the library's rule), so the pipeline fill / drain of one step hides behind the copies of the next.
+    # Every step still uploads its own inputs and downloads its own results (a second pair of pinned output buffers).
+    # If the box cannot give the extra contexts or pinned memory, the single-pair figure stands.
+    e2e_val, e2e_outputs_ok, e2e_mode = e2e_single_val, None, "single context pair (the second pair could not be set up)"
+    extra_ctx, extra_pin = [], []
+    try:
+        ctx_e2 = capi.Context(W_, H_, CH_, LEVELS_, max_batch=B, device=local); extra_ctx.append(ctx_e2)
+        ctx_d2 = capi.Context(W_, H_, CH_, LEVELS_, max_batch=B, device=local); extra_ctx.append(ctx_d2)
+        h_ar2, p5 = pinned_array(L, nb_ar); extra_pin.append(p5)
+        h_dst2, p6 = pinned_array(L, nb_px); extra_pin.append(p6)
+        slots = [(ctx, ctx_d, h_ar, h_dst), (ctx_e2, ctx_d2, h_ar2, h_dst2)]
+
+        def issue(i):
+            ce, cd, ha, hd = slots[i & 1]  # (the *_stream calls wait for the slot's previous call themselves)
+            rc = L.ric_encode_u8_stream(ce.h, h_src.ctypes.data, B, q, ha.ctypes.data, null_cb, None)
+            _check(L, rc or L.ric_decode_u8_stream(cd.h, h_dec_in.ctypes.data, B, q, hd.ctypes.data, null_cb, None))
+
+        def drain():
+            for ce, cd, _, _ in slots:
+                _check(L, L.ric_sync(ce.h) or L.ric_sync(cd.h))
+        issue(0); issue(1); drain()
+        ok2 = 1.0
+    except Exception:
+        ok2 = 0.0
+    ok2 = -max_over_ranks(-ok2, dev)  # min over ranks: every rank runs the same variant
+    if ok2 > 0.5:
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            issue(i)
+        drain()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_val = 2.0 * pixels_per_step * args.e2e_steps / max_over_ranks(e2e_s, dev) / 1e6
+        e2e_outputs_ok = bool((h_ar2 == h_ar).all() and (h_dst2 == h_dst).all())
+        e2e_mode = "consecutive steps alternate between two context pairs, ric_sync at the end"
+    for c_ in [ctx_d] + extra_ctx:
+        c_.close()
+    for p_ in extra_pin:
+        L.ric_host_free(p_)
     h2d = nb_px + nb_ar
     d2h = nb_ar + nb_px
     # the box's roof for exactly these copies (no kernels): what e2e could reach if the GPU work were free
@@ -642,8 +682,10 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": L0_FWD_BYTES_PER_SAMPLE * S},
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps,
-                    "api": "ric_encode_u8_stream + ric_decode_u8_stream on two contexts, then ric_sync (pinned host buffers; "
-                           "both PCIe directions busy at once)",
+                    "api": "ric_encode_u8_stream + ric_decode_u8_stream (pinned host buffers, both PCIe directions busy at once); " + e2e_mode,
+                    "single_call_value": e2e_single_val,
+                    "single_call_api": "the same two calls on one context pair, ric_sync after every step",
+                    "outputs_equal_across_slots": e2e_outputs_ok,
                     "sequential_value": e2e_seq_val,
                     "sequential_api": "ric_encode_u8 then ric_decode_u8, blocking, one context",
                     "copy_only_value": copy_roof_val,

@@ -777,7 +777,11 @@ static cudaError_t copy_pixels(void *dst, size_t dpitch, const void *src, size_t
 	return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
 }
 
-static int chunk_images(int n) { return n >= 12 ? (n + 7) / 8 : n >= 4 ? 2 : 1; }
+static int chunk_images(int n)
+{
+	static const int parts = getenv("RIC_CHUNKS", 8);  // chunks per call of the pipelined host-buffer paths
+	return n >= 12 ? (n + parts - 1) / parts : n >= 4 ? 2 : 1;
+}
 
 static int sync_pipe(ric_ctx *c)
 {
